@@ -1,0 +1,35 @@
+// tcgen05 GEMM for every dense contraction of the CASync generator (1x1 convs, Linear, dense 3x3 convs
+// as implicit GEMM, the decoder's first 1x1 with bilinear-upsample + skip-concat fused into the A
+// producer).  C[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 operands, fp32 accumulation in TMEM.
+#pragma once
+#include "common.cuh"
+
+namespace casync {
+
+enum AMode : int { A_PLAIN = 0, A_CONV3X3 = 1, A_UPCAT = 2 };
+
+struct GemmArgs {
+  int amode;
+  const __nv_bfloat16* A;   // PLAIN: [M, lda]; CONV3X3: NHWC [B,Hin,Win,Cin]; UPCAT: low-res NHWC [B,Hin,Win,Cin]
+  const __nv_bfloat16* A2;  // UPCAT: skip NHWC [B,Hout,Wout,K-Cin]
+  int lda;
+  int M, K, N;
+  int Hin, Win, Cin, Hout, Wout, stride, pad;
+  const uint8_t* W;         // packed: k-block kb, row n -> 128 B (64 bf16, SWIZZLE_128B image) at (kb*N+n)*128
+  const float* bias;        // [N]
+  const float* rscale;      // [N] or null: v += rscale[n] * res_pre[m,n]   (before the activation)
+  const __nv_bfloat16* res_pre;
+  int ld_rpre;
+  int leaky;                // LeakyReLU(0.01) after bias/res_pre
+  const __nv_bfloat16* res_post;  // added after the activation (InvertedResidual skip, module/unet.py:38)
+  int ld_rpost;
+  const float* post_scale;  // optional trailing BN + LeakyReLU (audio bn7, module/unet.py:193)
+  const float* post_shift;
+  __nv_bfloat16* C;
+  int ldc;
+};
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);  // returns 0 or cudaError
+int gemm_init();                                          // set smem attributes (once per process)
+
+}  // namespace casync

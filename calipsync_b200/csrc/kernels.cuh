@@ -1,0 +1,41 @@
+// CUDA-core kernels of the CASync generator forward: everything that is not a dense contraction.
+#pragma once
+#include "common.cuh"
+
+namespace casync {
+
+// `inc` (InConvDw, module/unet.py:58-67): one InvertedResidual 6 -> (12) -> 32 at 160x160, fully fused on
+// CUDA cores (K=6/12 is far below a UMMA tile).  Weights travel as kernel parameters (constant bank).
+struct IncParams {
+  float w1[12 * 6];   // [hidden][cin], BN folded
+  float b1[12];
+  float wd[9 * 12];   // [tap][hidden]
+  float bd[12];
+  float w2[32 * 12];  // [cout][hidden]
+  float b2[32];
+};
+struct OutcParams {   // OutConv + outc_bn folded (module/unet.py:100-106, 342-343)
+  float w[3 * 32];
+  float b[3];
+  float pad_;
+};
+
+int launch_inc(const float* x_nchw, __nv_bfloat16* x1_nhwc, const IncParams& w, int batch, cudaStream_t st);
+// depthwise 3x3, pad 1, stride 1|2, + folded BN bias + LeakyReLU.  NHWC bf16 -> NHWC bf16, wd fp32 [9][C].
+int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
+                 int W, int C, int stride, cudaStream_t st);
+// audio window fp32 [B,32,32,32] NCHW -> bf16 NHWC
+int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st);
+// softmax(q k^T) v core of CrossAttention (module/unet.py:209-217) for one attention block:
+//   out[m, c] = gamma * sum_j softmax_j(q[m,:].k[j,:]) v[j,c] + x[m,c]   (per frame: 100 queries x 100 keys)
+int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
+                     const __nv_bfloat16* x, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st);
+// kx = leaky(bn_kx(tx + ox0 + ox1 + ox2 + ox3))  (module/unet.py:329-336), fp32 sum of the bf16 stage tensors
+int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,
+                const __nv_bfloat16* o3, const float* s, const float* t, __nv_bfloat16* kx, long rows,
+                cudaStream_t st);
+// sigmoid(outc_bn(outc(x)))  ->  fp32 NCHW [B,3,160,160] or uint8 HWC floor(p*255)
+int launch_outc(const __nv_bfloat16* x, void* out, const OutcParams& w, int batch, int u8_hwc, cudaStream_t st);
+int kernels_init();
+
+}  // namespace casync
