@@ -1,0 +1,373 @@
+// CUDA-core kernels (sm_100a): fused `inc` block, depthwise 3x3, audio layout change, attention core,
+// stage sum + BN, output head.  All activations NHWC bf16, all arithmetic fp32.
+#include "kernels.cuh"
+
+namespace casync {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// inc: 32x8 output tile per CTA, 34x10 input halo.  The depthwise conv zero-pads the HIDDEN tensor
+// (module/unet.py:21-27), so hidden values of out-of-image halo pixels are exactly 0, not pw1(0).
+// ------------------------------------------------------------------------------------------------
+constexpr int kIncTW = 32, kIncTH = 8, kIncHW = kIncTW + 2, kIncHH = kIncTH + 2, kIncHalo = kIncHW * kIncHH;
+
+__global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                  const __grid_constant__ IncParams w) {
+  __shared__ float s_in[6][kIncHalo];
+  __shared__ float s_h[12][kIncHalo];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * kIncTW, y0 = blockIdx.y * kIncTH, b = blockIdx.z;
+  const float* xb = x + (size_t)b * 6 * 25600;
+  for (int idx = tid; idx < 6 * kIncHalo; idx += 256) {
+    int c = idx / kIncHalo, r = idx - c * kIncHalo;
+    int yy = r / kIncHW, xx = r - yy * kIncHW;
+    int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+    float v = 0.f;
+    if (gy >= 0 && gy < 160 && gx >= 0 && gx < 160) v = __ldg(xb + (size_t)c * 25600 + gy * 160 + gx);
+    s_in[c][r] = v;
+  }
+  __syncthreads();
+  for (int r = tid; r < kIncHalo; r += 256) {
+    int yy = r / kIncHW, xx = r - yy * kIncHW;
+    int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+    bool inside = gy >= 0 && gy < 160 && gx >= 0 && gx < 160;
+    float in[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) in[c] = s_in[c][r];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      float a = w.b1[j];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a = fmaf(w.w1[j * 6 + c], in[c], a);
+      s_h[j][r] = inside ? leaky(a) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 5, tx = tid & 31;
+  float h2[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    float a = w.bd[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) a = fmaf(w.wd[(ky * 3 + kx) * 12 + j], s_h[j][(ty + ky) * kIncHW + tx + kx], a);
+    h2[j] = leaky(a);
+  }
+  __nv_bfloat16* o = out + ((size_t)b * 25600 + (size_t)(y0 + ty) * 160 + x0 + tx) * 32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int n = g * 8 + e;
+      float a = w.b2[n];
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a = fmaf(w.w2[n * 12 + j], h2[j], a);
+      v[e] = leaky(a);
+    }
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]);
+    q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]);
+    q.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(o)[g] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3: one thread = one output pixel x 8 channels (16 B), neighbours come from L1/L2.
+// ------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
+                                                    __nv_bfloat16* __restrict__ out, const float* __restrict__ wd,
+                                                    const float* __restrict__ bd, long total, int H, int W, int C,
+                                                    int Ho, int Wo) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  long pix = idx / c8n;
+  const int ox = (int)(pix % Wo);
+  pix /= Wo;
+  const int oy = (int)(pix % Ho);
+  const int b = (int)(pix / Ho);
+  const int c = c8 * 8;
+  float acc[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bd + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bd + c + 4));
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+  const __nv_bfloat16* ib = in + (size_t)b * H * W * C + c;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * STRIDE - 1 + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * STRIDE - 1 + kx;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(ib + ((size_t)iy * W + ix) * C));
+      const float* wp = wd + (ky * 3 + kx) * C + c;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[0] = fmaf(w0.x, bf16_lo(v.x), acc[0]);
+      acc[1] = fmaf(w0.y, bf16_hi(v.x), acc[1]);
+      acc[2] = fmaf(w0.z, bf16_lo(v.y), acc[2]);
+      acc[3] = fmaf(w0.w, bf16_hi(v.y), acc[3]);
+      acc[4] = fmaf(w1.x, bf16_lo(v.z), acc[4]);
+      acc[5] = fmaf(w1.y, bf16_hi(v.z), acc[5]);
+      acc[6] = fmaf(w1.z, bf16_lo(v.w), acc[6]);
+      acc[7] = fmaf(w1.w, bf16_hi(v.w), acc[7]);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(leaky(acc[0]), leaky(acc[1]));
+  o.y = pack_bf16(leaky(acc[2]), leaky(acc[3]));
+  o.z = pack_bf16(leaky(acc[4]), leaky(acc[5]));
+  o.w = pack_bf16(leaky(acc[6]), leaky(acc[7]));
+  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// audio window: fp32 [B,32(c),32,32] -> bf16 [B,32,32,32(c)]; one thread = one pixel (reads are coalesced
+// across the warp for every channel, the 64 B result is written with four 16 B stores).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) audio_prep_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ out,
+                                                         long npix) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const long b = p >> 10, r = p & 1023;
+  const float* src = a + b * 32768 + r;
+  uint32_t w[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) w[c] = pack_bf16(__ldg(src + (2 * c) * 1024), __ldg(src + (2 * c + 1) * 1024));
+  uint4* dst = reinterpret_cast<uint4*>(out + p * 32);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention core.  CTA = (channel quarter, frame), 10 warps; warp w owns query rows 10w..10w+9 as two
+// groups of 5.  S = q k^T and the row softmax stay in registers (lane owns keys lane+32t), P goes to
+// shared memory only for the warp's own rows, then O = P V over this CTA's 128 value channels.
+// Softmax has no 1/sqrt(d) scale (module/unet.py:212-213).
+// ------------------------------------------------------------------------------------------------
+constexpr int kT = 100;  // tokens per frame (10x10)
+struct AttnSmem {
+  uint32_t q2[kT][32];     // q[i][2d..2d+1] packed bf16x2
+  uint32_t kT2[32][kT];    // k[j][2d..2d+1] packed, transposed
+  uint2 v4[kT][32];        // v[j][4*lane..4*lane+3] (this CTA's 128 channels)
+  float P[kT][kT];
+};
+
+__global__ void __launch_bounds__(320) attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
+                                                        const __nv_bfloat16* __restrict__ k,
+                                                        const __nv_bfloat16* __restrict__ v, int ldkv,
+                                                        const __nv_bfloat16* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ out, float gamma) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = blockIdx.x;
+  const size_t row0 = (size_t)blockIdx.y * kT;
+  for (int idx = tid; idx < kT * 32; idx += 320) {
+    const int j = idx >> 5, d2 = idx & 31;
+    s.q2[j][d2] = __ldg(reinterpret_cast<const uint32_t*>(q + (row0 + j) * ldq) + d2);
+    s.kT2[d2][j] = __ldg(reinterpret_cast<const uint32_t*>(k + (row0 + j) * ldkv) + d2);
+    s.v4[j][d2] = __ldg(reinterpret_cast<const uint2*>(v + (row0 + j) * ldkv + quarter * 128) + d2);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int grp = 0; grp < 2; ++grp) {
+    const int i0 = warp * 10 + grp * 5;
+    float sc[5][4];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) sc[r][t] = 0.f;
+#pragma unroll 4
+    for (int d2 = 0; d2 < 32; ++d2) {
+      uint32_t kk[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) kk[t] = (lane + 32 * t < kT) ? s.kT2[d2][lane + 32 * t] : 0u;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const uint32_t qq = s.q2[i0 + r][d2];
+        const float ql = bf16_lo(qq), qh = bf16_hi(qq);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sc[r][t] = fmaf(qh, bf16_hi(kk[t]), fmaf(ql, bf16_lo(kk[t]), sc[r][t]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < kT) mx = fmaxf(mx, sc[r][t]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        sc[r][t] = (lane + 32 * t < kT) ? __expf(sc[r][t] - mx) : 0.f;
+        sum += sc[r][t];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < kT) s.P[i0 + r][lane + 32 * t] = sc[r][t] * inv;
+    }
+    __syncwarp();
+    float acc[5][4];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < kT; j += 4) {
+      float4 pr[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) pr[r] = *reinterpret_cast<const float4*>(&s.P[i0 + r][j]);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint2 vv = s.v4[j + jj][lane];
+        const float v0 = bf16_lo(vv.x), v1 = bf16_hi(vv.x), v2 = bf16_lo(vv.y), v3 = bf16_hi(vv.y);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float pp = jj == 0 ? pr[r].x : jj == 1 ? pr[r].y : jj == 2 ? pr[r].z : pr[r].w;
+          acc[r][0] = fmaf(pp, v0, acc[r][0]);
+          acc[r][1] = fmaf(pp, v1, acc[r][1]);
+          acc[r][2] = fmaf(pp, v2, acc[r][2]);
+          acc[r][3] = fmaf(pp, v3, acc[r][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const size_t off = (row0 + i0 + r) * 512 + quarter * 128 + lane * 4;
+      const uint2 xx = __ldg(reinterpret_cast<const uint2*>(x + off));
+      uint2 o;
+      o.x = pack_bf16(fmaf(gamma, acc[r][0], bf16_lo(xx.x)), fmaf(gamma, acc[r][1], bf16_hi(xx.x)));
+      o.y = pack_bf16(fmaf(gamma, acc[r][2], bf16_lo(xx.y)), fmaf(gamma, acc[r][3], bf16_hi(xx.y)));
+      *reinterpret_cast<uint2*>(out + off) = o;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sum5_kernel(const uint4* __restrict__ tx, const uint4* __restrict__ o0,
+                                                   const uint4* __restrict__ o1, const uint4* __restrict__ o2,
+                                                   const uint4* __restrict__ o3, const float* __restrict__ s,
+                                                   const float* __restrict__ t, uint4* __restrict__ kx, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int c = (int)(i & 127) * 8;  // 1024 channels = 128 chunks of 8
+  const uint4 a = __ldg(tx + i), b = __ldg(o0 + i), cc = __ldg(o1 + i), d = __ldg(o2 + i), e = __ldg(o3 + i);
+  const uint32_t *pa = &a.x, *pb = &b.x, *pc = &cc.x, *pd = &d.x, *pe = &e.x;
+  uint4 o;
+  uint32_t* po = &o.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float lo = bf16_lo(pa[j]) + bf16_lo(pb[j]) + bf16_lo(pc[j]) + bf16_lo(pd[j]) + bf16_lo(pe[j]);
+    float hi = bf16_hi(pa[j]) + bf16_hi(pb[j]) + bf16_hi(pc[j]) + bf16_hi(pd[j]) + bf16_hi(pe[j]);
+    lo = leaky(fmaf(__ldg(s + c + 2 * j), lo, __ldg(t + c + 2 * j)));
+    hi = leaky(fmaf(__ldg(s + c + 2 * j + 1), hi, __ldg(t + c + 2 * j + 1)));
+    po[j] = pack_bf16(lo, hi);
+  }
+  kx[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) outc_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out,
+                                                   const __grid_constant__ OutcParams w, long npix, int u8_hwc) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const uint4* src = reinterpret_cast<const uint4*>(x + p * 32);
+  float a0 = w.b[0], a1 = w.b[1], a2 = w.b[2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 v = __ldg(src + g);
+    const uint32_t* pv = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16_lo(pv[j]), hi = bf16_hi(pv[j]);
+      const int c = g * 8 + 2 * j;
+      a0 = fmaf(w.w[c + 1], hi, fmaf(w.w[c], lo, a0));
+      a1 = fmaf(w.w[32 + c + 1], hi, fmaf(w.w[32 + c], lo, a1));
+      a2 = fmaf(w.w[64 + c + 1], hi, fmaf(w.w[64 + c], lo, a2));
+    }
+  }
+  const float s0 = 1.f / (1.f + __expf(-a0)), s1 = 1.f / (1.f + __expf(-a1)), s2 = 1.f / (1.f + __expf(-a2));
+  if (u8_hwc) {  // floor(p*255) like `np.array(pred*255, dtype=np.uint8)` (infer_api.py:265-266)
+    uint8_t* o = reinterpret_cast<uint8_t*>(out) + p * 3;
+    o[0] = (uint8_t)(s0 * 255.f);
+    o[1] = (uint8_t)(s1 * 255.f);
+    o[2] = (uint8_t)(s2 * 255.f);
+  } else {
+    const long b = p / 25600, r = p - b * 25600;
+    float* o = reinterpret_cast<float*>(out) + b * 76800 + r;
+    o[0] = s0;
+    o[25600] = s1;
+    o[51200] = s2;
+  }
+}
+
+}  // namespace
+
+int kernels_init() {
+  return (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(AttnSmem));
+}
+
+int launch_inc(const float* x, __nv_bfloat16* out, const IncParams& w, int batch, cudaStream_t st) {
+  dim3 grid(160 / kIncTW, 160 / kIncTH, batch);
+  inc_kernel<<<grid, 256, 0, st>>>(x, out, w);
+  return (int)cudaGetLastError();
+}
+
+int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
+                 int W, int C, int stride, cudaStream_t st) {
+  const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
+  const long total = (long)batch * Ho * Wo * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (stride == 2) dw3x3_kernel<2><<<blocks, 256, 0, st>>>(in, out, wd, bd, total, H, W, C, Ho, Wo);
+  else dw3x3_kernel<1><<<blocks, 256, 0, st>>>(in, out, wd, bd, total, H, W, C, Ho, Wo);
+  return (int)cudaGetLastError();
+}
+
+int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st) {
+  const long npix = (long)batch * 1024;
+  audio_prep_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(audio, out, npix);
+  return (int)cudaGetLastError();
+}
+
+int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
+                     const __nv_bfloat16* x, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st) {
+  attention_kernel<<<dim3(4, batch), 320, sizeof(AttnSmem), st>>>(q, ldq, k, v, ldkv, x, out, gamma);
+  return (int)cudaGetLastError();
+}
+
+int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,
+                const __nv_bfloat16* o3, const float* s, const float* t, __nv_bfloat16* kx, long rows,
+                cudaStream_t st) {
+  const long n8 = rows * 128;
+  sum5_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(tx), reinterpret_cast<const uint4*>(o0), reinterpret_cast<const uint4*>(o1),
+      reinterpret_cast<const uint4*>(o2), reinterpret_cast<const uint4*>(o3), s, t, reinterpret_cast<uint4*>(kx), n8);
+  return (int)cudaGetLastError();
+}
+
+int launch_outc(const __nv_bfloat16* x, void* out, const OutcParams& w, int batch, int u8_hwc, cudaStream_t st) {
+  const long npix = (long)batch * 25600;
+  outc_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, out, w, npix, u8_hwc);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace casync

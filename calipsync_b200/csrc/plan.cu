@@ -1,0 +1,530 @@
+// Host side of the C ABI (include/casync_b200.h): packed-weight schema, workspace layout, and the launch
+// sequence of Model.forward (module/unet.py:314-345) over the sm_100a kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/casync_b200.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+using namespace casync;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---- InvertedResidual table (module/unet.py:8-40; instances :157-173, :286-299) ----------------------
+struct IrDef {
+  const char* name;  // reference module path
+  int cin, cout, h_in, stride, res;
+};
+const IrDef kIr[] = {
+    {"inc.inconv.0", 6, 32, 160, 1, 0},
+    {"down1.maxpool_conv.0.double_conv.0", 32, 64, 160, 2, 0},
+    {"down1.maxpool_conv.0.double_conv.1", 64, 64, 80, 1, 1},
+    {"down2.maxpool_conv.0.double_conv.0", 64, 128, 80, 2, 0},
+    {"down2.maxpool_conv.0.double_conv.1", 128, 128, 40, 1, 1},
+    {"down3.maxpool_conv.0.double_conv.0", 128, 256, 40, 2, 0},
+    {"down3.maxpool_conv.0.double_conv.1", 256, 256, 20, 1, 1},
+    {"down4.maxpool_conv.0.double_conv.0", 256, 512, 20, 2, 0},
+    {"down4.maxpool_conv.0.double_conv.1", 512, 512, 10, 1, 1},
+    {"audio_model.conv1", 32, 64, 32, 1, 0},
+    {"audio_model.conv2", 64, 128, 32, 1, 0},
+    {"audio_model.conv4", 256, 256, 16, 1, 1},
+    {"audio_model.conv6", 512, 512, 10, 1, 1},
+    {"audio_model.conv7", 512, 512, 10, 1, 1},
+    {"fuse_conv.0.double_conv.0", 1024, 512, 10, 1, 0},
+    {"fuse_conv.0.double_conv.1", 512, 512, 10, 1, 1},
+    {"fuse_conv.1.double_conv.0", 512, 256, 10, 1, 0},
+    {"fuse_conv.1.double_conv.1", 256, 256, 10, 1, 1},
+    {"up1.conv.double_conv.0", 512, 128, 20, 1, 0},
+    {"up1.conv.double_conv.1", 128, 128, 20, 1, 1},
+    {"up2.conv.double_conv.0", 256, 64, 40, 1, 0},
+    {"up2.conv.double_conv.1", 64, 64, 40, 1, 1},
+    {"up3.conv.double_conv.0", 128, 32, 80, 1, 0},
+    {"up3.conv.double_conv.1", 32, 32, 80, 1, 1},
+    {"up4.conv.double_conv.0", 64, 32, 160, 1, 0},
+    {"up4.conv.double_conv.1", 32, 32, 160, 1, 1},
+};
+constexpr int kNumIr = sizeof(kIr) / sizeof(kIr[0]);
+enum { IR_INC = 0, IR_DOWN = 1, IR_AUD1 = 9, IR_AUD2 = 10, IR_AUD4 = 11, IR_AUD6 = 12, IR_AUD7 = 13, IR_FUSE = 14, IR_UP = 18 };
+
+size_t packed_bytes(int n, int k) { return (size_t)((k + 63) / 64) * n * 128; }
+
+// ---- weight schema ------------------------------------------------------------------------------------
+struct Entry {
+  std::string name;
+  size_t bytes;
+};
+const std::vector<Entry>& schema() {
+  static std::vector<Entry> s;
+  if (!s.empty()) return s;
+  s.push_back({"inc.inconv.0|inc", sizeof(IncParams)});
+  for (int i = 1; i < kNumIr; ++i) {
+    const IrDef& d = kIr[i];
+    const int hid = 2 * d.cin;
+    const std::string p = std::string(d.name) + "|";
+    s.push_back({p + "w1", packed_bytes(hid, d.cin)});
+    s.push_back({p + "b1", (size_t)hid * 4});
+    s.push_back({p + "wd", (size_t)9 * hid * 4});
+    s.push_back({p + "bd", (size_t)hid * 4});
+    s.push_back({p + "w2", packed_bytes(d.cout, hid)});
+    s.push_back({p + "b2", (size_t)d.cout * 4});
+  }
+  s.push_back({"audio_model.conv3|w", packed_bytes(256, 9 * 128)});
+  s.push_back({"audio_model.conv3|b", 256 * 4});
+  s.push_back({"audio_model.conv5|w", packed_bytes(512, 9 * 256)});
+  s.push_back({"audio_model.conv5|b", 512 * 4});
+  s.push_back({"audio_model.bn7|s", 512 * 4});
+  s.push_back({"audio_model.bn7|t", 512 * 4});
+  s.push_back({"mlp_fusion.fc1|w", packed_bytes(1024, 1024)});
+  s.push_back({"mlp_fusion.fc1|b", 1024 * 4});
+  s.push_back({"mlp_fusion.fc2|w", packed_bytes(1024, 1024)});
+  s.push_back({"mlp_fusion.fc2|b", 1024 * 4});
+  s.push_back({"mlp_fusion.fc2|rs", 1024 * 4});
+  s.push_back({"attention_blocks|kv_w", packed_bytes(4 * 576, 512)});
+  s.push_back({"attention_blocks|kv_b", 4 * 576 * 4});
+  s.push_back({"attention_blocks|gamma", 4 * 4});
+  for (int j = 0; j < 4; ++j) {
+    const std::string p = "attention_blocks." + std::to_string(j) + "|";
+    s.push_back({p + "p1_w", packed_bytes(512, 1024)});
+    s.push_back({p + "p1_b", 512 * 4});
+    s.push_back({p + "q_w", packed_bytes(64, 512)});
+    s.push_back({p + "q_b", 64 * 4});
+    s.push_back({p + "b1_w", packed_bytes(1024, 512)});
+    s.push_back({p + "b1_b", 1024 * 4});
+    s.push_back({p + "b1_rs", 1024 * 4});
+  }
+  s.push_back({"bn_kx|s", 1024 * 4});
+  s.push_back({"bn_kx|t", 1024 * 4});
+  s.push_back({"outc|outc", sizeof(OutcParams)});
+  return s;
+}
+int entry_index(const std::string& name) {
+  static const std::unordered_map<std::string, int> idx = [] {
+    std::unordered_map<std::string, int> m;
+    const auto& s = schema();
+    for (size_t i = 0; i < s.size(); ++i) m[s[i].name] = (int)i;
+    return m;
+  }();
+  auto it = idx.find(name);
+  return it == idx.end() ? -1 : it->second;
+}
+
+// ---- workspace buffers (per frame: rows x cols bf16) ------------------------------------------------------
+struct BufDef {
+  const char* name;
+  int rows, cols;
+};
+const BufDef kBufs[] = {
+    {"x1", 25600, 32},  {"x2", 6400, 64},    {"x3", 1600, 128},  {"x4", 400, 256},   {"cat", 100, 1024},
+    {"d1t", 6400, 64},  {"d2t", 1600, 128},  {"d3t", 400, 256},  {"d4t", 100, 512},  {"aud_in", 1024, 32},
+    {"a1", 1024, 64},   {"a2", 1024, 128},   {"a3", 256, 256},   {"a4", 256, 256},   {"a5", 100, 512},
+    {"a6", 100, 512},   {"fc1", 100, 1024},  {"tx", 100, 1024},  {"kvall", 100, 2304}, {"p1", 100, 512},
+    {"q", 100, 64},     {"att", 100, 512},   {"ox0", 100, 1024}, {"ox1", 100, 1024}, {"ox2", 100, 1024},
+    {"ox3", 100, 1024}, {"kx", 100, 1024},   {"f0", 100, 512},   {"f1", 100, 512},   {"f2", 100, 256},
+    {"fuse", 100, 256}, {"t_up1", 400, 128}, {"up1", 400, 128},  {"t_up2", 1600, 64}, {"up2", 1600, 64},
+    {"t_up3", 6400, 32}, {"up3", 6400, 32},  {"t_up4", 25600, 32}, {"up4", 25600, 32},
+    {"h1", 25600, 128}, {"h2", 25600, 128},
+};
+constexpr int kNumBufs = sizeof(kBufs) / sizeof(kBufs[0]);
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct casync_plan {
+  const uint8_t* dev = nullptr;
+  std::vector<int64_t> off;
+  IncParams inc;
+  OutcParams outc;
+  float gamma[4];
+  int chunk = 256;
+  template <class T>
+  const T* w(const std::string& name) const {
+    int i = entry_index(name);
+    return i < 0 ? nullptr : reinterpret_cast<const T*>(dev + off[i]);
+  }
+};
+
+namespace {
+
+struct Workspace {
+  uint8_t* base;
+  size_t offs[kNumBufs];
+  size_t total;
+  Workspace(void* ws, int frames) : base(reinterpret_cast<uint8_t*>(ws)) {
+    size_t o = 0;
+    for (int i = 0; i < kNumBufs; ++i) {
+      offs[i] = o;
+      o += align256((size_t)kBufs[i].rows * kBufs[i].cols * 2 * frames);
+    }
+    total = o;
+  }
+  int index(const char* name) const {
+    for (int i = 0; i < kNumBufs; ++i)
+      if (!strcmp(kBufs[i].name, name)) return i;
+    return -1;
+  }
+  bf16* operator[](const char* name) const { return reinterpret_cast<bf16*>(base + offs[index(name)]); }
+};
+
+#define CK(expr)                                                                          \
+  do {                                                                                    \
+    int e_ = (expr);                                                                      \
+    if (e_) return fail(CASYNC_ECUDA, "%s failed: %s", #expr, cudaGetErrorString((cudaError_t)e_)); \
+  } while (0)
+
+// One InvertedResidual: pw1 GEMM (+BN+leaky) -> depthwise 3x3 (+BN+leaky) -> pw2 GEMM (+BN+leaky, +skip,
+// optional trailing BN).  `up_low` != null selects the decoder A producer: in = cat([up(up_low), in]).
+int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf16* out, int ldc, bf16* h1, bf16* h2,
+           const float* post_s, const float* post_t, int batch, cudaStream_t st) {
+  const IrDef& d = kIr[idx];
+  const std::string pre = std::string(d.name) + "|";
+  const int hid = 2 * d.cin, H = d.h_in, Ho = d.stride == 2 ? H / 2 : H;
+  GemmArgs g{};
+  g.M = batch * H * H;
+  g.K = d.cin;
+  g.N = hid;
+  g.W = p->w<uint8_t>(pre + "w1");
+  g.bias = p->w<float>(pre + "b1");
+  g.leaky = 1;
+  g.C = h1;
+  g.ldc = hid;
+  if (up_low) {
+    g.amode = A_UPCAT;
+    g.A = up_low;
+    g.A2 = in;
+    g.Cin = d.cin / 2;
+    g.Hin = g.Win = H / 2;
+    g.Hout = g.Wout = H;
+  } else {
+    g.amode = A_PLAIN;
+    g.A = in;
+    g.lda = d.cin;
+  }
+  CK(launch_gemm(g, st));
+  CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
+  GemmArgs g2{};
+  g2.amode = A_PLAIN;
+  g2.A = h2;
+  g2.lda = hid;
+  g2.M = batch * Ho * Ho;
+  g2.K = hid;
+  g2.N = d.cout;
+  g2.W = p->w<uint8_t>(pre + "w2");
+  g2.bias = p->w<float>(pre + "b2");
+  g2.leaky = 1;
+  if (d.res) {
+    g2.res_post = in;
+    g2.ld_rpost = d.cin;
+  }
+  g2.post_scale = post_s;
+  g2.post_shift = post_t;
+  g2.C = out;
+  g2.ldc = ldc;
+  CK(launch_gemm(g2, st));
+  return 0;
+}
+
+int run_dense(const casync_plan* p, const char* wname, const char* bname, const bf16* A, int lda, int M, int K, int N,
+              bf16* C, int ldc, int leaky, const bf16* res_pre, int ld_rpre, const char* rsname, cudaStream_t st) {
+  GemmArgs g{};
+  g.amode = A_PLAIN;
+  g.A = A;
+  g.lda = lda;
+  g.M = M;
+  g.K = K;
+  g.N = N;
+  g.W = p->w<uint8_t>(wname);
+  g.bias = p->w<float>(bname);
+  g.leaky = leaky;
+  if (res_pre) {
+    g.res_pre = res_pre;
+    g.ld_rpre = ld_rpre;
+    g.rscale = p->w<float>(rsname);
+  }
+  g.C = C;
+  g.ldc = ldc;
+  CK(launch_gemm(g, st));
+  return 0;
+}
+
+int run_conv3x3(const casync_plan* p, const char* pre, const bf16* in, int Hin, int Cin, int pad, int Cout, bf16* out,
+                int batch, cudaStream_t st) {
+  GemmArgs g{};
+  g.amode = A_CONV3X3;
+  g.A = in;
+  g.Hin = g.Win = Hin;
+  g.Cin = Cin;
+  g.stride = 2;
+  g.pad = pad;
+  g.Hout = g.Wout = (Hin + 2 * pad - 3) / 2 + 1;
+  g.M = batch * g.Hout * g.Wout;
+  g.K = 9 * Cin;
+  g.N = Cout;
+  g.W = p->w<uint8_t>(std::string(pre) + "|w");
+  g.bias = p->w<float>(std::string(pre) + "|b");
+  g.leaky = 1;
+  g.C = out;
+  g.ldc = Cout;
+  CK(launch_gemm(g, st));
+  return 0;
+}
+
+// AudioConvHubert.forward (module/unet.py:177-194); result (after bn7 + leaky) -> out[., ldo]
+int run_audio(const casync_plan* p, const float* audio, bf16* out, int ldo, const Workspace& w, int batch,
+              cudaStream_t st) {
+  CK(launch_audio_prep(audio, w["aud_in"], batch, st));
+  int e;
+  if ((e = run_ir(p, IR_AUD1, w["aud_in"], nullptr, w["a1"], 64, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD2, w["a1"], nullptr, w["a2"], 128, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_conv3x3(p, "audio_model.conv3", w["a2"], 32, 128, 1, 256, w["a3"], batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD4, w["a3"], nullptr, w["a4"], 256, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_conv3x3(p, "audio_model.conv5", w["a4"], 16, 256, 3, 512, w["a5"], batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD6, w["a5"], nullptr, w["a6"], 512, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  return run_ir(p, IR_AUD7, w["a6"], nullptr, out, ldo, w["h1"], w["h2"], p->w<float>("audio_model.bn7|s"),
+                p->w<float>("audio_model.bn7|t"), batch, st);
+}
+
+// module/unet.py:323-336: tx = bn_tx(cat + mlp(cat)); 4 x AttentionBlock; kx = leaky(bn_kx(tx + sum ox_i)).
+// `cat` = [x5 | audio] with leading dimension 1024.
+int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const Workspace& w, int batch,
+                         cudaStream_t st) {
+  const int M = batch * 100;
+  int e;
+  if ((e = run_dense(p, "mlp_fusion.fc1|w", "mlp_fusion.fc1|b", cat, 1024, M, 1024, 1024, w["fc1"], 1024, 1, nullptr, 0,
+                     nullptr, st))) return e;
+  if ((e = run_dense(p, "mlp_fusion.fc2|w", "mlp_fusion.fc2|b", w["fc1"], 1024, M, 1024, 1024, w["tx"], 1024, 0, cat,
+                     1024, "mlp_fusion.fc2|rs", st))) return e;
+  // keys/values of all four blocks depend only on the audio half of `cat`: one GEMM, N = 4*(64+512)
+  if ((e = run_dense(p, "attention_blocks|kv_w", "attention_blocks|kv_b", cat + 512, 1024, M, 512, 2304, w["kvall"],
+                     2304, 0, nullptr, 0, nullptr, st))) return e;
+  const char* oxn[4] = {"ox0", "ox1", "ox2", "ox3"};
+  const bf16* ox = w["tx"];
+  for (int j = 0; j < 4; ++j) {
+    const std::string pre = "attention_blocks." + std::to_string(j) + "|";
+    if ((e = run_dense(p, (pre + "p1_w").c_str(), (pre + "p1_b").c_str(), ox, 1024, M, 1024, 512, w["p1"], 512, 0,
+                       nullptr, 0, nullptr, st))) return e;
+    if ((e = run_dense(p, (pre + "q_w").c_str(), (pre + "q_b").c_str(), w["p1"], 512, M, 512, 64, w["q"], 64, 0, nullptr,
+                       0, nullptr, st))) return e;
+    CK(launch_attention(w["q"], 64, w["kvall"] + j * 576, w["kvall"] + j * 576 + 64, 2304, w["p1"], w["att"],
+                        p->gamma[j], batch, st));
+    if ((e = run_dense(p, (pre + "b1_w").c_str(), (pre + "b1_b").c_str(), w["att"], 512, M, 512, 1024, w[oxn[j]], 1024, 1,
+                       w["tx"], 1024, (pre + "b1_rs").c_str(), st))) return e;
+    ox = w[oxn[j]];
+  }
+  CK(launch_sum5(w["tx"], w["ox0"], w["ox1"], w["ox2"], w["ox3"], p->w<float>("bn_kx|s"), p->w<float>("bn_kx|t"), kx,
+                 M, st));
+  return 0;
+}
+
+int run_up(const casync_plan* p, int level, const bf16* low, const bf16* skip, bf16* tmp, bf16* out,
+           const Workspace& w, int batch, cudaStream_t st) {
+  const int i0 = IR_UP + 2 * (level - 1);
+  int e;
+  if ((e = run_ir(p, i0, skip, low, tmp, kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  return run_ir(p, i0 + 1, tmp, nullptr, out, kIr[i0 + 1].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st);
+}
+
+int forward_chunk(const casync_plan* p, const float* x, const float* audio, void* out, const Workspace& w, int batch,
+                  unsigned flags, cudaStream_t st) {
+  int e;
+  CK(launch_inc(x, w["x1"], p->inc, batch, st));
+  const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
+  const char* dn_o[4] = {"x2", "x3", "x4", "cat"};
+  const bf16* cur = w["x1"];
+  for (int l = 0; l < 4; ++l) {
+    const int i0 = IR_DOWN + 2 * l;
+    if ((e = run_ir(p, i0, cur, nullptr, w[dn_t[l]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+    const int ldo = l == 3 ? 1024 : kIr[i0 + 1].cout;  // x5 lands in the left half of `cat`
+    if ((e = run_ir(p, i0 + 1, w[dn_t[l]], nullptr, w[dn_o[l]], ldo, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+    cur = w[dn_o[l]];
+  }
+  if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st))) return e;
+  if ((e = run_fusion_attention(p, w["cat"], w["kx"], w, batch, st))) return e;
+  const char* fz[5] = {"kx", "f0", "f1", "f2", "fuse"};
+  for (int l = 0; l < 4; ++l)
+    if ((e = run_ir(p, IR_FUSE + l, w[fz[l]], nullptr, w[fz[l + 1]], kIr[IR_FUSE + l].cout, w["h1"], w["h2"], nullptr,
+                    nullptr, batch, st))) return e;
+  if ((e = run_up(p, 1, w["fuse"], w["x4"], w["t_up1"], w["up1"], w, batch, st))) return e;
+  if ((e = run_up(p, 2, w["up1"], w["x3"], w["t_up2"], w["up2"], w, batch, st))) return e;
+  if ((e = run_up(p, 3, w["up2"], w["x2"], w["t_up3"], w["up3"], w, batch, st))) return e;
+  if ((e = run_up(p, 4, w["up3"], w["x1"], w["t_up4"], w["up4"], w, batch, st))) return e;
+  CK(launch_outc(w["up4"], out, p->outc, batch, (flags & CASYNC_F_OUT_U8_HWC) ? 1 : 0, st));
+  return 0;
+}
+
+int check_device() {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return fail(CASYNC_ECUDA, "no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  if (prop.major != 10)
+    return fail(CASYNC_EDEVICE, "casync_b200 needs compute capability 10.x (sm_100a); device %d is %d.%d", dev,
+                prop.major, prop.minor);
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* casync_version(void) { return "casync_b200 0.1 (sm_100a; tcgen05 + bulk-async)"; }
+const char* casync_last_error(void) { return g_err; }
+
+int casync_weight_entry_count(void) { return (int)schema().size(); }
+int casync_weight_entry(int index, const char** name, size_t* bytes) {
+  const auto& s = schema();
+  if (index < 0 || index >= (int)s.size()) return fail(CASYNC_EINVAL, "weight entry %d out of range", index);
+  if (name) *name = s[index].name.c_str();
+  if (bytes) *bytes = s[index].bytes;
+  return 0;
+}
+
+int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_bytes, const int64_t* offsets,
+                       int n_entries, casync_plan** out) {
+  if (!host_blob || !dev_blob || !offsets || !out) return fail(CASYNC_EINVAL, "null argument");
+  const auto& s = schema();
+  if (n_entries != (int)s.size()) return fail(CASYNC_EINVAL, "expected %d weight entries, got %d", (int)s.size(), n_entries);
+  for (int i = 0; i < n_entries; ++i)
+    if (offsets[i] < 0 || (offsets[i] & 255) || (size_t)offsets[i] + s[i].bytes > blob_bytes)
+      return fail(CASYNC_EINVAL, "bad offset for entry %s", s[i].name.c_str());
+  int e = check_device();
+  if (e) return e;
+  CK(gemm_init());
+  CK(kernels_init());
+  casync_plan* p = new casync_plan;
+  p->dev = reinterpret_cast<const uint8_t*>(dev_blob);
+  p->off.assign(offsets, offsets + n_entries);
+  const uint8_t* hb = reinterpret_cast<const uint8_t*>(host_blob);
+  memcpy(&p->inc, hb + offsets[entry_index("inc.inconv.0|inc")], sizeof(IncParams));
+  memcpy(&p->outc, hb + offsets[entry_index("outc|outc")], sizeof(OutcParams));
+  memcpy(p->gamma, hb + offsets[entry_index("attention_blocks|gamma")], sizeof p->gamma);
+  if (const char* c = getenv("CASYNC_CHUNK")) {
+    int v = atoi(c);
+    if (v > 0) p->chunk = v;
+  }
+  *out = p;
+  return 0;
+}
+
+void casync_plan_destroy(casync_plan* plan) { delete plan; }
+
+int casync_chunk_frames(const casync_plan* plan) { return plan ? plan->chunk : 0; }
+
+size_t casync_workspace_bytes(const casync_plan* plan, int batch) {
+  if (!plan || batch <= 0) return 0;
+  return Workspace(nullptr, batch < plan->chunk ? batch : plan->chunk).total;
+}
+size_t casync_stage_scratch_bytes(const casync_plan* plan, int batch) { return casync_workspace_bytes(plan, batch); }
+
+int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
+  if (!plan || batch <= 0) return 0;
+  const int64_t per_chunk = 1 + 25 * 3 + 1 + 2 + 3 + 4 * 4 + 1 + 1;
+  return per_chunk * ((batch + plan->chunk - 1) / plan->chunk);
+}
+
+int casync_forward(const casync_plan* plan, const float* x, const float* audio, void* out, void* workspace, int batch,
+                   unsigned flags, void* stream) {
+  if (!plan || !x || !audio || !out || !workspace) return fail(CASYNC_EINVAL, "null argument");
+  if (batch <= 0) return fail(CASYNC_EINVAL, "batch must be positive, got %d", batch);
+  if (flags & CASYNC_F_FP32) return fail(CASYNC_EUNSUP, "fp32 arithmetic path is not implemented");
+  if ((uintptr_t)workspace & 255) return fail(CASYNC_EINVAL, "workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t out_frame = (flags & CASYNC_F_OUT_U8_HWC) ? 76800 : 76800 * 4;
+  for (int f0 = 0; f0 < batch; f0 += plan->chunk) {
+    const int nb = batch - f0 < plan->chunk ? batch - f0 : plan->chunk;
+    Workspace w(workspace, batch < plan->chunk ? batch : plan->chunk);
+    int e = forward_chunk(plan, x + (size_t)f0 * 6 * 25600, audio + (size_t)f0 * 32768,
+                          reinterpret_cast<uint8_t*>(out) + (size_t)f0 * out_frame, w, nb, flags, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int casync_stage_view(const casync_plan* plan, int batch, const char* name, size_t* offset, int64_t* rows,
+                      int64_t* cols, int64_t* ld) {
+  if (!plan || !name || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "stage views need batch <= chunk");
+  Workspace w(nullptr, batch);
+  std::string n = name;
+  const char* buf = name;
+  size_t extra = 0;
+  int64_t c = -1, l = -1;
+  if (n == "x5") { buf = "cat"; c = 512; l = 1024; }
+  else if (n == "audio") { buf = "cat"; c = 512; l = 1024; extra = 512 * 2; }
+  int i = w.index(buf);
+  if (i < 0) return fail(CASYNC_EINVAL, "unknown stage '%s'", name);
+  if (offset) *offset = w.offs[i] + extra;
+  if (rows) *rows = (int64_t)kBufs[i].rows * batch;
+  if (cols) *cols = c > 0 ? c : kBufs[i].cols;
+  if (ld) *ld = l > 0 ? l : kBufs[i].cols;
+  return 0;
+}
+
+int casync_ir_count(void) { return kNumIr; }
+int casync_ir_info(int i, const char** name, int* cin, int* cout, int* h_in, int* stride, int* residual) {
+  if (i < 0 || i >= kNumIr) return fail(CASYNC_EINVAL, "ir index %d out of range", i);
+  if (name) *name = kIr[i].name;
+  if (cin) *cin = kIr[i].cin;
+  if (cout) *cout = kIr[i].cout;
+  if (h_in) *h_in = kIr[i].h_in;
+  if (stride) *stride = kIr[i].stride;
+  if (residual) *residual = kIr[i].res;
+  return 0;
+}
+
+int casync_ir_block(const casync_plan* plan, int ir_index, const void* in, void* out, void* scratch, int batch,
+                    void* stream) {
+  if (!plan || !in || !out || !scratch || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "bad argument");
+  if (ir_index < 1 || ir_index >= kNumIr)
+    return fail(CASYNC_EINVAL, "ir index %d not runnable here (0 = inc takes the fp32 NCHW input)", ir_index);
+  if (ir_index >= IR_UP && !((ir_index - IR_UP) & 1))
+    return fail(CASYNC_EINVAL, "decoder block %d consumes (low, skip): use casync_up_block", ir_index);
+  Workspace w(scratch, batch);
+  return run_ir(plan, ir_index, reinterpret_cast<const bf16*>(in), nullptr, reinterpret_cast<bf16*>(out),
+                kIr[ir_index].cout, w["h1"], w["h2"], nullptr, nullptr, batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int casync_audio_cnn(const casync_plan* plan, const float* audio, void* out, void* scratch, int batch, void* stream) {
+  if (!plan || !audio || !out || !scratch || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "bad argument");
+  Workspace w(scratch, batch);
+  return run_audio(plan, audio, reinterpret_cast<bf16*>(out), 512, w, batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int casync_fusion_attention(const casync_plan* plan, const void* x5, const void* audio, void* kx, void* scratch,
+                            int batch, void* stream) {
+  if (!plan || !x5 || !audio || !kx || !scratch || batch <= 0 || batch > plan->chunk)
+    return fail(CASYNC_EINVAL, "bad argument");
+  Workspace w(scratch, batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)batch * 100;
+  CK(cudaMemcpy2DAsync(w["cat"], 2048, x5, 1024, 1024, rows, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpy2DAsync(w["cat"] + 512, 2048, audio, 1024, 1024, rows, cudaMemcpyDeviceToDevice, st));
+  return run_fusion_attention(plan, w["cat"], reinterpret_cast<bf16*>(kx), w, batch, st);
+}
+
+int casync_up_block(const casync_plan* plan, int level, const void* low, const void* skip, void* out, void* scratch,
+                    int batch, void* stream) {
+  if (!plan || !low || !skip || !out || !scratch || batch <= 0 || batch > plan->chunk || level < 1 || level > 4)
+    return fail(CASYNC_EINVAL, "bad argument");
+  Workspace w(scratch, batch);
+  const char* tmp[4] = {"t_up1", "t_up2", "t_up3", "t_up4"};
+  return run_up(plan, level, reinterpret_cast<const bf16*>(low), reinterpret_cast<const bf16*>(skip), w[tmp[level - 1]],
+                reinterpret_cast<bf16*>(out), w, batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

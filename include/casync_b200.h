@@ -20,6 +20,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define CASYNC_API __attribute__((visibility("default")))
+#else
+#define CASYNC_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -37,58 +43,58 @@ extern "C" {
 
 typedef struct casync_plan casync_plan;
 
-const char *casync_version(void);
-const char *casync_last_error(void);
+CASYNC_API const char *casync_version(void);
+CASYNC_API const char *casync_last_error(void);
 
 /* Packed-weight schema.  The host-side packer (calipsync_b200/packer.py) asks the library which entries
  * it expects, in which order and of what byte size, folds BatchNorm (module/unet.py:18,28,32 ...) into
  * them and writes them back to back into one blob at 256-byte aligned offsets. */
-int casync_weight_entry_count(void);
-int casync_weight_entry(int index, const char **name, size_t *bytes);
+CASYNC_API int casync_weight_entry_count(void);
+CASYNC_API int casync_weight_entry(int index, const char **name, size_t *bytes);
 
 /* Replaces: Model.__init__ + load_state_dict + .to(device) (infer_api.py:41-43).  `host_blob` and
  * `dev_blob` hold the same `blob_bytes` bytes (host copy is read only during this call; the device copy
  * must outlive the plan).  `offsets[i]` is the byte offset of schema entry i. */
-int casync_plan_create(const void *host_blob, const void *dev_blob, size_t blob_bytes, const int64_t *offsets,
+CASYNC_API int casync_plan_create(const void *host_blob, const void *dev_blob, size_t blob_bytes, const int64_t *offsets,
                        int n_entries, casync_plan **out);
-void casync_plan_destroy(casync_plan *plan);
+CASYNC_API void casync_plan_destroy(casync_plan *plan);
 
 /* Frames processed per internal pass; workspace is sized for min(batch, chunk). */
-int casync_chunk_frames(const casync_plan *plan);
-size_t casync_workspace_bytes(const casync_plan *plan, int batch);
+CASYNC_API int casync_chunk_frames(const casync_plan *plan);
+CASYNC_API size_t casync_workspace_bytes(const casync_plan *plan, int batch);
 
 /* Replaces: Model.forward(x, audio_feat) (module/unet.py:314-345).
  *   x_nchw   fp32 [batch,6,160,160]   (cat([face, masked face]) in [0,1]; not modified)
  *   audio    fp32 [batch,32,32,32]    (HuBERT window; not modified)
  *   out      fp32 [batch,3,160,160] in (0,1), or uint8 [batch,160,160,3] with CASYNC_F_OUT_U8_HWC
  *   workspace  >= casync_workspace_bytes(plan, batch) bytes, 256-byte aligned, device memory */
-int casync_forward(const casync_plan *plan, const float *x_nchw, const float *audio, void *out, void *workspace,
+CASYNC_API int casync_forward(const casync_plan *plan, const float *x_nchw, const float *audio, void *out, void *workspace,
                    int batch, unsigned flags, void *stream);
 
 /* Stage activations left in `workspace` by the last casync_forward with batch <= casync_chunk_frames():
  * bf16 row-major [rows, cols] with leading dimension `ld` (elements) at byte `offset` (NHWC: rows =
  * batch*H*W pixels).  Names: x1..x5, audio, tx, ox0..ox3, kx, fuse, up1..up4 (oracle STAGE_NAMES). */
-int casync_stage_view(const casync_plan *plan, int batch, const char *name, size_t *offset, int64_t *rows,
+CASYNC_API int casync_stage_view(const casync_plan *plan, int batch, const char *name, size_t *offset, int64_t *rows,
                       int64_t *cols, int64_t *ld);
-int64_t casync_launches_per_forward(const casync_plan *plan, int batch);
+CASYNC_API int64_t casync_launches_per_forward(const casync_plan *plan, int batch);
 
 /* Per-stage entry points (unit tests / ncu).  Activations are NHWC bf16, `scratch` is device memory of
  * at least casync_stage_scratch_bytes(plan, batch).
  * casync_ir_block: one InvertedResidual (module/unet.py:8-40); `ir_index` as listed by casync_ir_info. */
-int casync_ir_count(void);
-int casync_ir_info(int ir_index, const char **name, int *cin, int *cout, int *h_in, int *stride, int *residual);
-size_t casync_stage_scratch_bytes(const casync_plan *plan, int batch);
-int casync_ir_block(const casync_plan *plan, int ir_index, const void *in_nhwc, void *out_nhwc, void *scratch,
+CASYNC_API int casync_ir_count(void);
+CASYNC_API int casync_ir_info(int ir_index, const char **name, int *cin, int *cout, int *h_in, int *stride, int *residual);
+CASYNC_API size_t casync_stage_scratch_bytes(const casync_plan *plan, int batch);
+CASYNC_API int casync_ir_block(const casync_plan *plan, int ir_index, const void *in_nhwc, void *out_nhwc, void *scratch,
                     int batch, void *stream);
 /* AudioConvHubert (module/unet.py:147-194): fp32 [B,32,32,32] NCHW -> bf16 [B*100, 512] */
-int casync_audio_cnn(const casync_plan *plan, const float *audio, void *out_nhwc, void *scratch, int batch,
+CASYNC_API int casync_audio_cnn(const casync_plan *plan, const float *audio, void *out_nhwc, void *scratch, int batch,
                      void *stream);
 /* MLP fusion + bn_tx + 4 attention blocks + bn_kx (module/unet.py:323-336): x5, audio bf16 [B*100,512]
  * -> kx bf16 [B*100,1024] */
-int casync_fusion_attention(const casync_plan *plan, const void *x5, const void *audio, void *kx, void *scratch,
+CASYNC_API int casync_fusion_attention(const casync_plan *plan, const void *x5, const void *audio, void *kx, void *scratch,
                             int batch, void *stream);
 /* Up (module/unet.py:82-97), level 1..4: low [B,h,w,C] + skip [B,2h,2w,C] -> [B,2h,2w,Cout] */
-int casync_up_block(const casync_plan *plan, int level, const void *low, const void *skip, void *out, void *scratch,
+CASYNC_API int casync_up_block(const casync_plan *plan, int level, const void *low, const void *skip, void *out, void *scratch,
                     int batch, void *stream);
 
 #ifdef __cplusplus

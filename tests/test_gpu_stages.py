@@ -1,0 +1,95 @@
+"""Per-stage entry points of the C ABI, each fed with ORACLE inputs so errors cannot hide behind (or be blamed
+on) upstream stages.  Compared with the oracle's sub-functions (module/unet.py sub-modules)."""
+import ctypes
+
+import pytest
+import torch
+
+from calipsync_b200 import Model, _lib
+from oracle import casync_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1.2e-2     # rel-L2 of one block in bf16 (inputs rounded to bf16 + bf16 hidden tensors)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    sd = O.make_state_dict(0, "R1")
+    m = Model(6, "hubert")
+    m.load_state_dict(sd)
+    m = m.to("cuda:0").eval()
+    x, a = O.make_inputs(2, 0)
+    m(x.cuda(), a.cuda())                      # creates the plan
+    _, st = O.forward(sd, x, a, return_stages=True)
+    lib = _lib.load()
+    scratch = torch.empty(lib.casync_stage_scratch_bytes(m._plan[0], 2), dtype=torch.uint8, device="cuda")
+    return dict(sd=sd, m=m, x=x, a=a, st=st, lib=lib, scratch=scratch, plan=m._plan[0])
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def nchw(t, b, h, c):
+    return t.float().cpu().reshape(b, h, h, c).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3, 4, 7, 8, 9, 11, 13, 14, 17, 19, 21, 23, 25])
+def test_inverted_residual_block(ctx, idx):
+    d = _lib.ir_table()[idx]
+    g = torch.Generator().manual_seed(idx)
+    xin = (torch.randn(2, d["cin"], d["h_in"], d["h_in"], generator=g) * 0.3).bfloat16().float()
+    ref = O.inverted_residual(ctx["sd"], d["name"], xin, d["stride"], bool(d["residual"]))
+    ho = d["h_in"] // d["stride"]
+    out = torch.empty(2 * ho * ho, d["cout"], dtype=torch.bfloat16, device="cuda")
+    rc = ctx["lib"].casync_ir_block(ctx["plan"], idx, nhwc(xin).data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "casync_ir_block")
+    torch.cuda.synchronize()
+    err = O.rel_l2(nchw(out, 2, ho, d["cout"]), ref)
+    assert err < TOL, (d["name"], err)
+
+
+def test_audio_cnn(ctx):
+    out = torch.empty(200, 512, dtype=torch.bfloat16, device="cuda")
+    rc = ctx["lib"].casync_audio_cnn(ctx["plan"], ctx["a"].cuda().data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "casync_audio_cnn")
+    torch.cuda.synchronize()
+    assert O.rel_l2(nchw(out, 2, 10, 512), ctx["st"]["audio"]) < 2e-2
+
+
+def test_fusion_attention(ctx):
+    st = ctx["st"]
+    kx = torch.empty(200, 1024, dtype=torch.bfloat16, device="cuda")
+    rc = ctx["lib"].casync_fusion_attention(ctx["plan"], nhwc(st["x5"]).data_ptr(), nhwc(st["audio"]).data_ptr(),
+                                            kx.data_ptr(), ctx["scratch"].data_ptr(), 2,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "casync_fusion_attention")
+    torch.cuda.synchronize()
+    assert O.rel_l2(nchw(kx, 2, 10, 1024), st["kx"]) < 2e-2
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4])
+def test_up_block(ctx, level):
+    st = ctx["st"]
+    low = st[("fuse", "up1", "up2", "up3")[level - 1]]
+    skip = st[("x4", "x3", "x2", "x1")[level - 1]]
+    ref = O.up_block(ctx["sd"], "up%d" % level, low.bfloat16().float(), skip.bfloat16().float())
+    h, c = ref.shape[2], ref.shape[1]
+    out = torch.empty(2 * h * h, c, dtype=torch.bfloat16, device="cuda")
+    rc = ctx["lib"].casync_up_block(ctx["plan"], level, nhwc(low).data_ptr(), nhwc(skip).data_ptr(), out.data_ptr(),
+                                    ctx["scratch"].data_ptr(), 2,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "casync_up_block")
+    torch.cuda.synchronize()
+    assert O.rel_l2(nchw(out, 2, h, c), ref) < 2e-2
+
+
+def test_bad_arguments_return_codes(ctx):
+    lib = ctx["lib"]
+    assert lib.casync_ir_block(ctx["plan"], 0, 1, 1, 1, 2, None) == -1       # inc is not runnable standalone
+    assert lib.casync_ir_block(ctx["plan"], 99, 1, 1, 1, 2, None) == -1
+    assert b"ir index" in lib.casync_last_error()
+    assert lib.casync_forward(ctx["plan"], None, None, None, None, 1, 0, None) == -1
+    assert lib.casync_forward(ctx["plan"], 256, 256, 256, 256, 1, _lib.F_FP32, None) == -4
