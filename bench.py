@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- CASync UNet forward throughput on B200 (BASELINE.json metric: UNet frames/s, 160x160, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one forward pass of the hot path over one batch of synthetic frames per GPU (BASELINE configs[1]:
+batch 64, bf16, random-init weights).  Frames are independent, so ranks run disjoint batches with no data-path
+collective ("scaling": "weak"); `value` = frames all ranks processed / max-over-ranks device time.
+
+Printed keys (one JSON line, rank 0): the contract's keys plus
+  roofline      dominant kernel of the step: algorithmic bytes|flops per launch / CUDA-event time per launch
+  cpu_baseline  the oracle port (torch fp32, CPU) timed on this box's host cores on a bounded sample
+  e2e           same metric through Model.forward with pinned HOST buffers (H2D + forward + D2H every step)
+  stages        per-kernel time split of one profiled step (CUDA events after every launch)
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port: the reference itself is
+Python and does not exist on the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "unet_frames_per_sec_160x160_bf16", "frames/s"
+FLOP_PER_FRAME = 7.9017e9          # 2 x 3.95086 GMAC
+L2_BYTES = 126e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1] = 64)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(rows)}
+
+
+def cpu_reference_fps(batch, iters, warmup):
+    """The oracle port (reference algorithm, torch fp32 on the host cores).  The one place bench.py runs oracle/."""
+    import torch
+    from oracle import casync_oracle as O
+    sd = O.make_state_dict(0, "R1")
+    x, a = O.make_inputs(batch, 0)
+    for _ in range(warmup):
+        O.forward(sd, x, a)
+    ts = []
+    for _ in range(iters):
+        t = time.perf_counter()
+        O.forward(sd, x, a)
+        ts.append(time.perf_counter() - t)
+    ts.sort()
+    return batch / ts[len(ts) // 2], torch.get_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: CPU implementation of the path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import casync_oracle as O
+    sample = 8                                    # frames per step: a bounded sample of the 64-frame batch
+    sd = O.make_state_dict(0, "R1")
+    x, a = O.make_inputs(sample, 0)
+    for _ in range(args.warmup):
+        O.forward(sd, x, a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.forward(sd, x, a)
+    dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    cores = torch.get_num_threads()
+    desc = "oracle port of module/unet.py forward, fp32 torch CPU, %d of the %d frames per step" % (sample, args.batch)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "CASync UNet forward, batch %d/GPU, 160x160 (BASELINE configs[1])" % args.batch,
+                   "sample_frames_per_step": sample, "host_cpus": os.cpu_count()},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def build_model(device):
+    import torch
+    from calipsync_b200 import Model
+    torch.manual_seed(0)
+    net = Model(6, "hubert")                       # random-init weights of the reference architecture
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():                          # healthy BN statistics + live attention path (SURVEY §4 regime R1)
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.75 + 0.5 * torch.rand(m.running_var.shape, generator=g))
+                m.weight.copy_(0.75 + 0.5 * torch.rand(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+        for blk in net.attention_blocks:
+            blk.cross_attention.gamma.fill_(0.5)
+    return net.to(device).eval()
+
+
+def synth_inputs(batch, device, seed):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.rand(batch, 6, 160, 160, device=device, generator=g)
+    x[:, 3:6, 5:150, 5:155] = 0.0                  # the reference's mouth mask (infer_api.py:239)
+    a = torch.randn(batch, 32, 32, 32, device=device, generator=g)
+    return x, a
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pk, pk_kind = peaks()
+
+    net = build_model(device)
+    B = args.batch
+    frame_in_bytes = (6 * 160 * 160 + 32 * 32 * 32) * 4
+    nsets = max(2, int(1.5 * L2_BYTES / (B * frame_in_bytes)) + 1)   # rotate input sets: total input bytes > L2
+    sets = [synth_inputs(B, device, 100 + rank * 1000 + i) for i in range(nsets)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        t1 = time.time()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    # ---- device-resident throughput (value) ------------------------------------------------------------------------
+    def step_dev(i):
+        x, a = sets[i % nsets]
+        net(x, a)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, t0, t1 = timed(step_dev, args.steps, max(3, args.warmup))
+    clocks = sampler.stop(t0, t1) if sampler else None
+    fps = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers (e2e) ---------------------------------------------------
+    host_sets = [(x.cpu().pin_memory(), a.cpu().pin_memory()) for x, a in sets[:2]]
+    host_out = [torch.empty(B, 3, 160, 160, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def step_e2e(i):
+        hx, ha = host_sets[i % 2]
+        out = net(hx.to(device, non_blocking=True), ha.to(device, non_blocking=True))
+        host_out[i % 2].copy_(out, non_blocking=True)
+
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    fps_e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel split of one step and the roofline of the dominant kernel (rank 0) -----------------------------
+    net.profile(*sets[0])
+    acc = {}
+    reps = 3
+    for r in range(reps):
+        for rec in net.profile(*sets[(r + 1) % nsets]):
+            a = acc.setdefault(rec["name"], dict(ms=0.0, flops=rec["flops"], bytes=rec["bytes"]))
+            a["ms"] += rec["ms"] / reps
+    total_ms = sum(v["ms"] for v in acc.values())
+    hbm_peak, tc_peak = pk["hbm_gbs"], pk["bf16_tflops"]      # burst peaks: each launch is timed between its own events
+    stages = []
+    for name, v in sorted(acc.items(), key=lambda kv: -kv[1]["ms"]):
+        t = v["ms"] / 1e3
+        gbs, tfs = v["bytes"] / t / 1e9, v["flops"] / t / 1e12
+        bound = "tensor" if v["flops"] / max(v["bytes"], 1) > tc_peak * 1e12 / (hbm_peak * 1e9) else "hbm"
+        stages.append({"kernel": name, "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "bound": bound,
+                       "gbs": round(gbs, 1), "tflops": round(tfs, 2),
+                       "frac": round(tfs / tc_peak if bound == "tensor" else gbs / hbm_peak, 4)})
+    top = stages[0]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top["kernel"])
+    except Exception:
+        pass
+    roofline = {"kernel": top["kernel"], "bound": top["bound"],
+                "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
+                "peak": tc_peak if top["bound"] == "tensor" else hbm_peak,
+                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json (burst)" if pk_kind == "measured" else "fallback (B200_PROFILING.md)",
+                "share_of_step": top["share"],
+                "whole_step": {"tflops": round(fps / world * FLOP_PER_FRAME / 1e12, 1),
+                               "frac_of_sustained_bf16": round(fps / world * FLOP_PER_FRAME / 1e12 /
+                                                               pk.get("bf16_tflops_sustained", tc_peak), 4)}}
+
+    sweep = {}
+    if not args.no_sweep and world == 1:
+        for b in (1, 8, 256, 1024):
+            try:
+                xs = [synth_inputs(b, device, 7 + i) for i in range(2 if b >= 256 else 8)]
+                n = max(3, min(20, 4096 // b))
+                m, _, _ = timed(lambda i: net(*xs[i % len(xs)]), n, 3)
+                sweep[str(b)] = round(b * n / (m / 1e3), 1)
+                del xs
+            except Exception as e:      # report, never hide
+                sweep[str(b)] = "error: %s" % e
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, cores = cpu_reference_fps(8, 8, 2)
+        v1, _ = cpu_reference_fps(1, 10, 3)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle port (torch fp32 CPU): batch 8 x 8 iters (median); batch 1: %.2f frames/s; host cpus %d"
+                         % (v1, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "CASync UNet forward, batch %d/GPU, 160x160 (BASELINE configs[1]), random-init weights" % B,
+                   "frames_per_step": world * B, "parallelism": "frame-sharded dp%d, no data-path collective" % world,
+                   "l2_policy": "%d rotating input sets (%.0f MB > L2); per-step activations %.1f GB >> L2"
+                                % (nsets, nsets * B * frame_in_bytes / 1e6, B * 25e6 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": B * frame_in_bytes, "d2h_bytes_per_step": B * 3 * 160 * 160 * 4,
+                "ms_per_step": ms_e2e / args.steps, "api": "Model.forward(x, audio_feat) fp32 in / fp32 out, pinned host buffers"},
+        "gpu_launches": net.launches_per_forward(B) * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "stages": stages[:12], "batch_sweep_frames_per_s": sweep,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

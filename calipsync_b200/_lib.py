@@ -32,6 +32,15 @@ SYMBOLS = [
     ("casync_up_block", _I, [_P, _I, _P, _P, _P, _P, _I, _P]),
 ]
 
+
+
+class LaunchRecord(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_float), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+SYMBOLS.append(("casync_forward_profiled", _I,
+                [_P, _P, _P, _P, _P, _I, C.c_uint, _P, C.POINTER(LaunchRecord), _I, C.POINTER(_I)]))
+
 _lib = None
 
 

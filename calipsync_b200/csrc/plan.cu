@@ -26,6 +26,36 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- optional per-launch profiling (casync_forward_profiled): one CUDA event after every launch -------------
+struct Prof {
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<casync_launch_record> recs;
+};
+thread_local Prof* g_prof = nullptr;
+void prof_mark(const char* label, double flops, double bytes) {
+  if (!g_prof) return;
+  casync_launch_record r{};
+  snprintf(r.name, sizeof r.name, "%s", label);
+  r.flops = flops;
+  r.bytes = bytes;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, g_prof->st);
+  g_prof->ev.push_back(e);
+  g_prof->recs.push_back(r);
+}
+std::string short_name(const char* ref_path) {  // "down1.maxpool_conv.0.double_conv.0" -> "down1.0"
+  std::string n = ref_path, out;
+  size_t dot = n.find('.');
+  out = n.substr(0, dot);
+  if (n.find("audio_model.") == 0) return "audio." + n.substr(12);
+  if (n.find("inc") == 0) return "inc";
+  out += n.substr(n.size() - 2);
+  if (n.find("fuse_conv.") == 0) out = "fuse" + n.substr(10, 1) + n.substr(n.size() - 2);
+  return out;
+}
+
 // ---- InvertedResidual table (module/unet.py:8-40; instances :157-173, :286-299) ----------------------
 struct IrDef {
   const char* name;  // reference module path
@@ -216,7 +246,10 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     g.lda = d.cin;
   }
   CK(launch_gemm(g, st));
+  const std::string sn = short_name(d.name);
+  prof_mark((sn + ".pw1").c_str(), 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
   CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
+  prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
   GemmArgs g2{};
   g2.amode = A_PLAIN;
   g2.A = h2;
@@ -236,6 +269,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.C = out;
   g2.ldc = ldc;
   CK(launch_gemm(g2, st));
+  prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
   return 0;
 }
 
@@ -259,6 +293,7 @@ int run_dense(const casync_plan* p, const char* wname, const char* bname, const 
   g.C = C;
   g.ldc = ldc;
   CK(launch_gemm(g, st));
+  prof_mark(wname, 2.0 * M * K * N, 2.0 * M * (K + N * (res_pre ? 2 : 1)));
   return 0;
 }
 
@@ -281,6 +316,7 @@ int run_conv3x3(const casync_plan* p, const char* pre, const bf16* in, int Hin, 
   g.C = out;
   g.ldc = Cout;
   CK(launch_gemm(g, st));
+  prof_mark(pre, 2.0 * g.M * g.K * g.N, 2.0 * (batch * Hin * Hin * Cin + (double)g.M * Cout));
   return 0;
 }
 
@@ -288,6 +324,7 @@ int run_conv3x3(const casync_plan* p, const char* pre, const bf16* in, int Hin, 
 int run_audio(const casync_plan* p, const float* audio, bf16* out, int ldo, const Workspace& w, int batch,
               cudaStream_t st) {
   CK(launch_audio_prep(audio, w["aud_in"], batch, st));
+  prof_mark("audio.prep", 0, 6.0 * batch * 32768);
   int e;
   if ((e = run_ir(p, IR_AUD1, w["aud_in"], nullptr, w["a1"], 64, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
   if ((e = run_ir(p, IR_AUD2, w["a1"], nullptr, w["a2"], 128, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
@@ -322,12 +359,15 @@ int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const 
                        0, nullptr, st))) return e;
     CK(launch_attention(w["q"], 64, w["kvall"] + j * 576, w["kvall"] + j * 576 + 64, 2304, w["p1"], w["att"],
                         p->gamma[j], batch, st));
+    prof_mark(("attn" + std::to_string(j) + ".core").c_str(), 2.0 * batch * (100.0 * 100 * 64 + 100.0 * 100 * 512),
+              2.0 * batch * 100 * (64 + 576 + 512 + 512));
     if ((e = run_dense(p, (pre + "b1_w").c_str(), (pre + "b1_b").c_str(), w["att"], 512, M, 512, 1024, w[oxn[j]], 1024, 1,
                        w["tx"], 1024, (pre + "b1_rs").c_str(), st))) return e;
     ox = w[oxn[j]];
   }
   CK(launch_sum5(w["tx"], w["ox0"], w["ox1"], w["ox2"], w["ox3"], p->w<float>("bn_kx|s"), p->w<float>("bn_kx|t"), kx,
                  M, st));
+  prof_mark("sum5_bn_kx", 0, 2.0 * M * 1024 * 6);
   return 0;
 }
 
@@ -343,6 +383,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
                   unsigned flags, cudaStream_t st) {
   int e;
   CK(launch_inc(x, w["x1"], p->inc, batch, st));
+  prof_mark("inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
   const char* dn_o[4] = {"x2", "x3", "x4", "cat"};
   const bf16* cur = w["x1"];
@@ -364,6 +405,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   if ((e = run_up(p, 3, w["up2"], w["x2"], w["t_up3"], w["up3"], w, batch, st))) return e;
   if ((e = run_up(p, 4, w["up3"], w["x1"], w["t_up4"], w["up4"], w, batch, st))) return e;
   CK(launch_outc(w["up4"], out, p->outc, batch, (flags & CASYNC_F_OUT_U8_HWC) ? 1 : 0, st));
+  prof_mark("outc.sigmoid", 2.0 * batch * 25600 * 96, batch * 25600.0 * (64 + ((flags & CASYNC_F_OUT_U8_HWC) ? 3 : 12)));
   return 0;
 }
 
@@ -453,6 +495,34 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
                           reinterpret_cast<uint8_t*>(out) + (size_t)f0 * out_frame, w, nb, flags, st);
     if (e) return e;
   }
+  return 0;
+}
+
+int casync_forward_profiled(const casync_plan* plan, const float* x, const float* audio, void* out, void* workspace,
+                            int batch, unsigned flags, void* stream, casync_launch_record* recs, int max_recs,
+                            int* n_recs) {
+  if (!recs || !n_recs || max_recs <= 0) return fail(CASYNC_EINVAL, "null argument");
+  Prof prof;
+  prof.st = reinterpret_cast<cudaStream_t>(stream);
+  g_prof = &prof;
+  prof_mark("<start>", 0, 0);
+  int e = casync_forward(plan, x, audio, out, workspace, batch, flags, stream);
+  g_prof = nullptr;
+  cudaError_t ce = cudaStreamSynchronize(prof.st);
+  int n = 0;
+  for (size_t i = 1; i < prof.ev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prof.ev[i - 1], prof.ev[i]);
+    if (n < max_recs) {
+      recs[n] = prof.recs[i];
+      recs[n].ms = ms;
+      ++n;
+    }
+  }
+  for (cudaEvent_t ev : prof.ev) cudaEventDestroy(ev);
+  *n_recs = n;
+  if (e) return e;
+  if (ce != cudaSuccess) return fail(CASYNC_ECUDA, "profiled forward: %s", cudaGetErrorString(ce));
   return 0;
 }
 

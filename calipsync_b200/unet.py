@@ -210,5 +210,23 @@ class Model(nn.Module):
         flat = ws[off.value: off.value + rows.value * ld.value * 2].view(torch.bfloat16)
         return torch.as_strided(flat, (rows.value, cols.value), (ld.value, 1))
 
+    @torch.no_grad()
+    def profile(self, x, audio_feat):
+        """One forward with a CUDA event after every launch -> list of dicts(name, ms, flops, bytes)."""
+        self._check_inputs(x, audio_feat)
+        out = torch.empty(x.shape[0], 3, 160, 160, dtype=torch.float32, device=x.device)
+        handle = self._ensure_plan(x.device)
+        ws = self._ensure_workspace(handle, x.shape[0], x.device)
+        recs = (_lib.LaunchRecord * 1024)()
+        n = ctypes.c_int()
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _lib.load().casync_forward_profiled(handle, x.contiguous().data_ptr(), audio_feat.contiguous().data_ptr(),
+                                                     out.data_ptr(), ws.data_ptr(), x.shape[0], _lib.F_BF16,
+                                                     ctypes.c_void_p(stream), recs, 1024, ctypes.byref(n))
+        _lib.check(rc, "casync_forward_profiled")
+        return [dict(name=recs[i].name.decode(), ms=recs[i].ms, flops=recs[i].flops, bytes=recs[i].bytes)
+                for i in range(n.value)]
+
     def launches_per_forward(self, batch):
         return int(_lib.load().casync_launches_per_forward(self._plan[0], batch)) if self._plan else 0

@@ -71,6 +71,19 @@ CASYNC_API size_t casync_workspace_bytes(const casync_plan *plan, int batch);
 CASYNC_API int casync_forward(const casync_plan *plan, const float *x_nchw, const float *audio, void *out, void *workspace,
                    int batch, unsigned flags, void *stream);
 
+/* Same as casync_forward, but records one CUDA event after every kernel launch, SYNCHRONISES the stream and
+ * returns per-launch device time with the launch's algorithmic FLOPs and activation bytes (weights excluded).
+ * Profiling aid for bench.py's roofline line; not for the timed throughput run. */
+typedef struct casync_launch_record {
+  char name[48];
+  float ms;
+  double flops;
+  double bytes;
+} casync_launch_record;
+CASYNC_API int casync_forward_profiled(const casync_plan *plan, const float *x_nchw, const float *audio, void *out,
+                                       void *workspace, int batch, unsigned flags, void *stream,
+                                       casync_launch_record *recs, int max_recs, int *n_recs);
+
 /* Stage activations left in `workspace` by the last casync_forward with batch <= casync_chunk_frames():
  * bf16 row-major [rows, cols] with leading dimension `ld` (elements) at byte `offset` (NHWC: rows =
  * batch*H*W pixels).  Names: x1..x5, audio, tx, ox0..ox3, kx, fuse, up1..up4 (oracle STAGE_NAMES). */

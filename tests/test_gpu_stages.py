@@ -42,7 +42,8 @@ def test_inverted_residual_block(ctx, idx):
     ref = O.inverted_residual(ctx["sd"], d["name"], xin, d["stride"], bool(d["residual"]))
     ho = d["h_in"] // d["stride"]
     out = torch.empty(2 * ho * ho, d["cout"], dtype=torch.bfloat16, device="cuda")
-    rc = ctx["lib"].casync_ir_block(ctx["plan"], idx, nhwc(xin).data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
+    xin_d = nhwc(xin)          # keep device inputs alive while the kernels run
+    rc = ctx["lib"].casync_ir_block(ctx["plan"], idx, xin_d.data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "casync_ir_block")
     torch.cuda.synchronize()
@@ -52,7 +53,8 @@ def test_inverted_residual_block(ctx, idx):
 
 def test_audio_cnn(ctx):
     out = torch.empty(200, 512, dtype=torch.bfloat16, device="cuda")
-    rc = ctx["lib"].casync_audio_cnn(ctx["plan"], ctx["a"].cuda().data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
+    a_d = ctx["a"].cuda()
+    rc = ctx["lib"].casync_audio_cnn(ctx["plan"], a_d.data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "casync_audio_cnn")
     torch.cuda.synchronize()
@@ -62,7 +64,8 @@ def test_audio_cnn(ctx):
 def test_fusion_attention(ctx):
     st = ctx["st"]
     kx = torch.empty(200, 1024, dtype=torch.bfloat16, device="cuda")
-    rc = ctx["lib"].casync_fusion_attention(ctx["plan"], nhwc(st["x5"]).data_ptr(), nhwc(st["audio"]).data_ptr(),
+    x5_d, au_d = nhwc(st["x5"]), nhwc(st["audio"])
+    rc = ctx["lib"].casync_fusion_attention(ctx["plan"], x5_d.data_ptr(), au_d.data_ptr(),
                                             kx.data_ptr(), ctx["scratch"].data_ptr(), 2,
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "casync_fusion_attention")
@@ -78,7 +81,8 @@ def test_up_block(ctx, level):
     ref = O.up_block(ctx["sd"], "up%d" % level, low.bfloat16().float(), skip.bfloat16().float())
     h, c = ref.shape[2], ref.shape[1]
     out = torch.empty(2 * h * h, c, dtype=torch.bfloat16, device="cuda")
-    rc = ctx["lib"].casync_up_block(ctx["plan"], level, nhwc(low).data_ptr(), nhwc(skip).data_ptr(), out.data_ptr(),
+    low_d, skip_d = nhwc(low), nhwc(skip)
+    rc = ctx["lib"].casync_up_block(ctx["plan"], level, low_d.data_ptr(), skip_d.data_ptr(), out.data_ptr(),
                                     ctx["scratch"].data_ptr(), 2,
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "casync_up_block")
