@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/casync_b200.h"
+#include "fused_ir.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -182,6 +183,10 @@ struct casync_plan {
   OutcParams outc;
   float gamma[4];
   int chunk = 256;
+  int num_sms = 148;
+  bool fuse_ir = true;
+  unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
+  int phase_dbg_ir = -1;
   template <class T>
   const T* w(const std::string& name) const {
     int i = entry_index(name);
@@ -224,6 +229,33 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   const IrDef& d = kIr[idx];
   const std::string pre = std::string(d.name) + "|";
   const int hid = 2 * d.cin, H = d.h_in, Ho = d.stride == 2 ? H / 2 : H;
+  if (p->fuse_ir && !post_s && ldc == d.cout && fused_ir_supported(d.cin, d.cout, d.stride, up_low != nullptr, d.res)) {
+    FusedArgs f{};
+    f.in = in;
+    f.low = up_low;
+    f.out = out;
+    f.ldo = ldc;
+    f.W1 = p->w<uint8_t>(pre + "w1");
+    f.W2 = p->w<uint8_t>(pre + "w2");
+    f.wd = p->w<float>(pre + "wd");
+    f.b1 = p->w<float>(pre + "b1");
+    f.bd = p->w<float>(pre + "bd");
+    f.b2 = p->w<float>(pre + "b2");
+    f.W = H;
+    f.batch = batch;
+    f.num_sms = p->num_sms;
+    f.cin = d.cin;
+    f.cout = d.cout;
+    f.stride = d.stride;
+    f.upcat = up_low != nullptr;
+    f.res = d.res;
+    f.dbg = (p->phase_dbg && p->phase_dbg_ir == idx) ? p->phase_dbg : nullptr;
+    CK(launch_fused_ir(f, st));
+    const double px_in = (double)batch * H * H, px_out = (double)batch * Ho * Ho;
+    prof_mark((short_name(d.name) + ".fused").c_str(), 2.0 * px_in * d.cin * hid + 18.0 * px_out * hid + 2.0 * px_out * hid * d.cout,
+              2.0 * (px_in * d.cin * (up_low ? 0.625 : 1.0) + px_out * d.cout * (d.res ? 2 : 1)));
+    return 0;
+  }
   GemmArgs g{};
   g.M = batch * H * H;
   g.K = d.cin;
@@ -456,6 +488,16 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   memcpy(&p->inc, hb + offsets[entry_index("inc.inconv.0|inc")], sizeof(IncParams));
   memcpy(&p->outc, hb + offsets[entry_index("outc|outc")], sizeof(OutcParams));
   memcpy(p->gamma, hb + offsets[entry_index("attention_blocks|gamma")], sizeof p->gamma);
+  {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) p->num_sms = sms;
+  }
+  if (const char* c = getenv("CASYNC_PHASE_DBG")) {   // developer aid: per-phase cycle counters of one fused block
+    p->phase_dbg_ir = atoi(c);
+    if (cudaMalloc(&p->phase_dbg, 64) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 64);
+  }
+  if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_CHUNK")) {
     int v = atoi(c);
     if (v > 0) p->chunk = v;
@@ -464,7 +506,21 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   return 0;
 }
 
-void casync_plan_destroy(casync_plan* plan) { delete plan; }
+void casync_plan_destroy(casync_plan* plan) {
+  if (plan && plan->phase_dbg) {
+    unsigned long long h[8] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, plan->phase_dbg, 64, cudaMemcpyDeviceToHost);
+    const char* names[7] = {"dw", "sync_a", "issue2+drain1", "epilogue", "produce_a1", "sync_b", "issue1"};
+    double tot = 0;
+    for (int i = 0; i < 7; ++i) tot += (double)h[i];
+    fprintf(stderr, "[casync phase dbg] ir %d:", plan->phase_dbg_ir);
+    for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
+    fprintf(stderr, "  (thread-0 cycles, all CTAs: %.3g)\n", tot);
+    cudaFree(plan->phase_dbg);
+  }
+  delete plan;
+}
 
 int casync_chunk_frames(const casync_plan* plan) { return plan ? plan->chunk : 0; }
 

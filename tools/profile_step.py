@@ -42,3 +42,4 @@ print({k: round(v, 3) for k, v in kinds.items()})
 if len(sys.argv) > 2:
     json.dump({"batch": B, "total_ms": tot, "launches": [dict(name=n, **acc[n]) for n in order], "peaks": pk},
               open(sys.argv[2], "w"), indent=1)
+net.repack()  # destroys the plan (prints developer phase timing when CASYNC_PHASE_DBG is set)
