@@ -495,7 +495,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   }
   if (const char* c = getenv("CASYNC_PHASE_DBG")) {   // developer aid: per-phase cycle counters of one fused block
     p->phase_dbg_ir = atoi(c);
-    if (cudaMalloc(&p->phase_dbg, 64) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 64);
+    if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
   }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_CHUNK")) {
@@ -508,15 +508,21 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
 
 void casync_plan_destroy(casync_plan* plan) {
   if (plan && plan->phase_dbg) {
-    unsigned long long h[8] = {0};
+    unsigned long long h[16] = {0};
     cudaDeviceSynchronize();
-    cudaMemcpy(h, plan->phase_dbg, 64, cudaMemcpyDeviceToHost);
-    const char* names[7] = {"dw", "sync_a", "issue2+drain1", "epilogue", "produce_a1", "sync_b", "issue1"};
-    double tot = 0;
-    for (int i = 0; i < 7; ++i) tot += (double)h[i];
-    fprintf(stderr, "[casync phase dbg] ir %d:", plan->phase_dbg_ir);
-    for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
-    fprintf(stderr, "  (thread-0 cycles, all CTAs: %.3g)\n", tot);
+    cudaMemcpy(h, plan->phase_dbg, 128, cudaMemcpyDeviceToHost);
+    const char* names[16] = {"I:wait_a1full", "I:wait_d1free", "I:issue1", "I:wait_a2full", "I:issue2", "B:wait_a1free",
+                             "B:produce", "B:wait_d1full", "B:wait_hidfree", "B:drain", "B:wait_d2full", "B:epilogue",
+                             "A:wait_hidfull", "A:wait_a2free", "A:dw", "misc"};
+    const int role_lo[3] = {0, 5, 12}, role_hi[3] = {5, 12, 15};
+    fprintf(stderr, "[casync phase dbg] ir %d (share of each role's own time):\n", plan->phase_dbg_ir);
+    for (int r = 0; r < 3; ++r) {
+      double tot = 0;
+      for (int i = role_lo[r]; i < role_hi[r]; ++i) tot += (double)h[i];
+      fprintf(stderr, "   ");
+      for (int i = role_lo[r]; i < role_hi[r]; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
+      fprintf(stderr, "  [%.3g cycles]\n", tot);
+    }
     cudaFree(plan->phase_dbg);
   }
   delete plan;
