@@ -2,6 +2,8 @@
 // stage sum + BN, output head.  All activations NHWC bf16, all arithmetic fp32.
 #include "kernels.cuh"
 
+#include <cuda_bf16.h>
+
 namespace casync {
 
 namespace {
@@ -77,59 +79,95 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3: one thread = one output pixel x 8 channels (16 B), neighbours come from L1/L2.
+// depthwise 3x3 (+ folded BN bias + LeakyReLU): thread = 8 channels (16 B) of one output column, walking
+// down kDwRows output rows with a sliding 3x3 window in registers (3 new 16 B loads per output at stride 1,
+// 6 at stride 2, instead of 9).  Packed bf16x2 FMAs, the same arithmetic as the fused kernel's depthwise.
 // ------------------------------------------------------------------------------------------------
+constexpr int kDwRows = 8;
+
 template <int STRIDE>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
                                                     __nv_bfloat16* __restrict__ out, const float* __restrict__ wd,
-                                                    const float* __restrict__ bd, long total, int H, int W, int C,
-                                                    int Ho, int Wo) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+                                                    const float* __restrict__ bd, int H, int W, int C, int Ho,
+                                                    int Wo) {
   const int c8n = C >> 3;
-  const int c8 = (int)(idx % c8n);
-  long pix = idx / c8n;
-  const int ox = (int)(pix % Wo);
-  pix /= Wo;
-  const int oy = (int)(pix % Ho);
-  const int b = (int)(pix / Ho);
-  const int c = c8 * 8;
-  float acc[8];
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int c8 = idx % c8n, ox = idx / c8n;
+  if (ox >= Wo) return;
+  const int c = c8 * 8, b = blockIdx.z;
+  const int oy0 = blockIdx.y * kDwRows;
+  const int oy1 = oy0 + kDwRows < Ho ? oy0 + kDwRows : Ho;
+  __nv_bfloat162 wt[9][4], wb[4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wd + t * C + c));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wd + t * C + c + 4));
+    wt[t][0] = __floats2bfloat162_rn(w0.x, w0.y);
+    wt[t][1] = __floats2bfloat162_rn(w0.z, w0.w);
+    wt[t][2] = __floats2bfloat162_rn(w1.x, w1.y);
+    wt[t][3] = __floats2bfloat162_rn(w1.z, w1.w);
+  }
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bd + c));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bd + c + 4));
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    wb[0] = __floats2bfloat162_rn(b0.x, b0.y);
+    wb[1] = __floats2bfloat162_rn(b0.z, b0.w);
+    wb[2] = __floats2bfloat162_rn(b1.x, b1.y);
+    wb[3] = __floats2bfloat162_rn(b1.z, b1.w);
   }
+  const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
   const __nv_bfloat16* ib = in + (size_t)b * H * W * C + c;
+  const int ix0 = ox * STRIDE - 1;
+  auto load_row = [&](int iy, uint4* r) {   // three horizontal taps of input row iy (zero outside the image)
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * STRIDE - 1 + ky;
-    if (iy < 0 || iy >= H) continue;
+    for (int k = 0; k < 3; ++k) {
+      const int ix = ix0 + k;
+      r[k] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                 ? __ldg(reinterpret_cast<const uint4*>(ib + ((size_t)iy * W + ix) * C))
+                 : make_uint4(0, 0, 0, 0);
+    }
+  };
+  auto taps = [&](__nv_bfloat162* a, const uint4* r, int trow) {
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * STRIDE - 1 + kx;
-      if (ix < 0 || ix >= W) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(ib + ((size_t)iy * W + ix) * C));
-      const float* wp = wd + (ky * 3 + kx) * C + c;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-      acc[0] = fmaf(w0.x, bf16_lo(v.x), acc[0]);
-      acc[1] = fmaf(w0.y, bf16_hi(v.x), acc[1]);
-      acc[2] = fmaf(w0.z, bf16_lo(v.y), acc[2]);
-      acc[3] = fmaf(w0.w, bf16_hi(v.y), acc[3]);
-      acc[4] = fmaf(w1.x, bf16_lo(v.z), acc[4]);
-      acc[5] = fmaf(w1.y, bf16_hi(v.z), acc[5]);
-      acc[6] = fmaf(w1.z, bf16_lo(v.w), acc[6]);
-      acc[7] = fmaf(w1.w, bf16_hi(v.w), acc[7]);
+    for (int k = 0; k < 3; ++k) {
+      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&r[k]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[trow * 3 + k][q], pv[q], a[q]);
+    }
+  };
+  uint4 r0[3], r1[3], r2[3];
+  if (STRIDE == 1) {
+    load_row(oy0 - 1, r0);
+    load_row(oy0, r1);
+  } else {
+    load_row(2 * oy0 - 1, r0);
+  }
+  for (int oy = oy0; oy < oy1; ++oy) {
+    if (STRIDE == 1) {
+      load_row(oy + 1, r2);
+    } else {
+      load_row(2 * oy, r1);
+      load_row(2 * oy + 1, r2);
+    }
+    __nv_bfloat162 a[4] = {wb[0], wb[1], wb[2], wb[3]};
+    taps(a, r0, 0);
+    taps(a, r1, 1);
+    taps(a, r2, 2);
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) po[q] = __hmax2(a[q], __hmul2(a[q], kslope));
+    *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (STRIDE == 1) {
+        r0[k] = r1[k];
+        r1[k] = r2[k];
+      } else {
+        r0[k] = r2[k];
+      }
     }
   }
-  uint4 o;
-  o.x = pack_bf16(leaky(acc[0]), leaky(acc[1]));
-  o.y = pack_bf16(leaky(acc[2]), leaky(acc[3]));
-  o.z = pack_bf16(leaky(acc[4]), leaky(acc[5]));
-  o.w = pack_bf16(leaky(acc[6]), leaky(acc[7]));
-  *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,10 +373,9 @@ int launch_inc(const float* x, __nv_bfloat16* out, const IncParams& w, int batch
 int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
                  int W, int C, int stride, cudaStream_t st) {
   const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
-  const long total = (long)batch * Ho * Wo * (C / 8);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
-  if (stride == 2) dw3x3_kernel<2><<<blocks, 256, 0, st>>>(in, out, wd, bd, total, H, W, C, Ho, Wo);
-  else dw3x3_kernel<1><<<blocks, 256, 0, st>>>(in, out, wd, bd, total, H, W, C, Ho, Wo);
+  const dim3 grid((unsigned)((Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kDwRows - 1) / kDwRows), (unsigned)batch);
+  if (stride == 2) dw3x3_kernel<2><<<grid, 256, 0, st>>>(in, out, wd, bd, H, W, C, Ho, Wo);
+  else dw3x3_kernel<1><<<grid, 256, 0, st>>>(in, out, wd, bd, H, W, C, Ho, Wo);
   return (int)cudaGetLastError();
 }
 

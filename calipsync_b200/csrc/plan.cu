@@ -185,6 +185,7 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
+  bool fuse_dw = false;  // (measured slower than the standalone kernel: off; CASYNC_FUSED_DW=1) depthwise 3x3 inside the projection GEMM (A_DW3X3) for blocks without a fully fused kernel
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
   int phase_dbg_ir = -1;
   template <class T>
@@ -280,12 +281,24 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   CK(launch_gemm(g, st));
   const std::string sn = short_name(d.name);
   prof_mark((sn + ".pw1").c_str(), 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
-  CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
-  prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
   GemmArgs g2{};
-  g2.amode = A_PLAIN;
-  g2.A = h2;
-  g2.lda = hid;
+  if (p->fuse_dw) {   // depthwise 3x3 + BN + leaky computed by the projection GEMM's A producers
+    g2.amode = A_DW3X3;
+    g2.A = h1;
+    g2.Hin = g2.Win = H;
+    g2.Cin = hid;
+    g2.Hout = g2.Wout = Ho;
+    g2.stride = d.stride;
+    g2.pad = 1;
+    g2.dw_w = p->w<float>(pre + "wd");
+    g2.dw_b = p->w<float>(pre + "bd");
+  } else {
+    CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
+    prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
+    g2.amode = A_PLAIN;
+    g2.A = h2;
+    g2.lda = hid;
+  }
   g2.M = batch * Ho * Ho;
   g2.K = hid;
   g2.N = d.cout;
@@ -301,7 +314,8 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.C = out;
   g2.ldc = ldc;
   CK(launch_gemm(g2, st));
-  prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
+  prof_mark((sn + (p->fuse_dw ? ".dw+pw2" : ".pw2")).c_str(), 2.0 * g2.M * g2.K * g2.N + (p->fuse_dw ? 18.0 * g2.M * hid : 0.0),
+            2.0 * ((p->fuse_dw ? (double)batch * H * H : (double)g2.M) * g2.K + (double)g2.M * g2.N * (d.res ? 2 : 1)));
   return 0;
 }
 
@@ -497,6 +511,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
     p->phase_dbg_ir = atoi(c);
     if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
   }
+  if (const char* c = getenv("CASYNC_FUSED_DW")) p->fuse_dw = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_CHUNK")) {
     int v = atoi(c);
@@ -538,7 +553,14 @@ size_t casync_stage_scratch_bytes(const casync_plan* plan, int batch) { return c
 
 int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
   if (!plan || batch <= 0) return 0;
-  const int64_t per_chunk = 1 + 25 * 3 + 1 + 2 + 3 + 4 * 4 + 1 + 1;
+  int64_t per_chunk = 1 /*inc*/ + 1 /*audio prep*/ + 2 /*conv3, conv5*/ + 3 /*fc1, fc2, kv*/ + 4 * 4 /*attention*/ + 1 + 1;
+  for (int i = 1; i < kNumIr; ++i) {
+    const IrDef& d = kIr[i];
+    const bool up = i >= IR_UP && !((i - IR_UP) & 1);
+    const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) &&
+                       fused_ir_supported(d.cin, d.cout, d.stride, up, d.res);
+    per_chunk += fused ? 1 : (plan->fuse_dw ? 2 : 3);
+  }
   return per_chunk * ((batch + plan->chunk - 1) / plan->chunk);
 }
 
