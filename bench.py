@@ -61,7 +61,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -110,6 +110,10 @@ def run_reference(args):
         return
     import torch
     from oracle import casync_oracle as O
+    try:                                          # torchrun exports OMP_NUM_THREADS=1: use every host thread we may
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     sample = 8                                    # frames per step: a bounded sample of the 64-frame batch
     sd = O.make_state_dict(0, "R1")
     x, a = O.make_inputs(sample, 0)
