@@ -7,7 +7,7 @@
 // 7 x ((8*TILES-1)/2).  The hidden channels are processed in chunks of 64 ("units" = patch x chunk) through a
 // double-buffered pipeline linked by mbarriers:
 //
-//   group B (8 warps)  A1[patch]  <- global (cp.async rows; decoder: bilinear x2 of the low-res tensor computed
+//   producers (4 warps) A1[patch] <- global (cp.async rows; decoder: bilinear x2 of the low-res tensor computed
 //                                    on the fly for the first Cin/2 channels + skip rows, module/unet.py:90-96)
 //   issuer  (1 thread) D1[u]      =  A1 . W1[chunk]^T                     tcgen05.mma  -> TMEM (fp32)
 //   group B            HID[u]     =  leaky(D1 + b1) as bf16, UMMA-swizzled smem; 0 outside the image (the
@@ -28,7 +28,9 @@ namespace casync {
 namespace {
 
 constexpr int kGroup = 256;                 // threads per compute group (8 warps)
-constexpr int kThreads = 2 * kGroup + 32;   // group B + group A + issuer warp
+constexpr int kProd = 128;                  // A1 producer threads (4 warps)
+constexpr int kIssuerWarp = (2 * kGroup + kProd) / 32;
+constexpr int kThreads = 2 * kGroup + kProd + 32;   // group B + group A + producers + issuer warp
 constexpr int kTile = 128 * 128;            // bytes of one 128-row x 128 B swizzled tile
 
 template <int CIN, int COUT, int STRIDE, int TILES, int A1BUFS>
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
   if (tid == 0) {
     mbar_init(bar(B_W), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(B_A1FULL + i), kGroup);
+      mbar_init(bar(B_A1FULL + i), kProd);
       mbar_init(bar(B_A1FREE + i), 1);
       mbar_init(bar(B_D1FULL + i), 1);
       mbar_init(bar(B_D1FREE + i), kGroup);
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     bulk_g2s(sBD, p.bd, CH * 4, bar(B_W));
     bulk_g2s(sB2, p.b2, COUT * 4, bar(B_W));
   }
-  if (warp == 16) {
+  if (warp == kIssuerWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
   const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
   // developer timing (CASYNC_PHASE_DBG): one thread per role accumulates cycles per activity slot
   long long tmark = p.dbg ? clock64() : 0;
-  const bool timed = p.dbg && (tid == 0 || tid == kGroup || tid == 2 * kGroup);
+  const bool timed = p.dbg && (tid == 0 || tid == kGroup || tid == 2 * kGroup || tid == kIssuerWarp * 32);
   auto T = [&](int slot) {
     if (timed) {
       const long long now = clock64();
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     }
   };
 
-  if (warp == 16) {
+  if (warp == kIssuerWarp) {
     // =========================================== MMA issuer ====================================================
     if (lane == 0 && n_mine > 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64), idesc2 = umma_idesc_bf16(128, COUT);
@@ -212,82 +214,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     }
   } else if (warp < 8) {
     // =========================================== group B: A1 producer, D1 drain, epilogue ======================
-    const int tB = tid;
-    auto produce_a1 = [&](int pi) {
-      const Patch q = decode(pi);
-      const int ab = pi % A1BUFS, ak = pi / A1BUFS;
-      T(15);
-      mbar_wait(bar(B_A1FREE + ab), (ak & 1) ^ 1);
-      T(5);
-      constexpr int TPR = kGroup / (TILES * 128);   // threads per window pixel
-      constexpr int NCH = CIN / 8;                  // 16-byte chunks per pixel
-      const int row = tB / TPR, sub = tB % TPR;
-      const int gy = q.GY0 + (row >> 4), gx = q.GX0 + (row & 15);
-      const bool inside = gy >= 0 && gy < W && gx >= 0 && gx < W;
-      const uint32_t a1 = sA1 + ab * C::kA1Buf + (row >> 7) * kTile;
-      const int r = row & 127;
-      if constexpr (!UPCAT) {
-        const __nv_bfloat16* src = p.in + ((size_t)(q.b * W + (inside ? gy : 0)) * W + (inside ? gx : 0)) * CIN;
-#pragma unroll
-        for (int c = sub; c < NCH; c += TPR)
-          cp_async16(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), src + c * 8, inside);
-      } else {
-        constexpr int C1 = CIN / 2;   // channels coming from the upsampled low-res tensor
-        const int h = W / 2;
-        const float sy = (float)(h - 1) / (float)(W - 1) * (float)(inside ? gy : 0);
-        const float sx = (float)(h - 1) / (float)(W - 1) * (float)(inside ? gx : 0);
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < h - 1 ? 1 : 0);
-        const float wy1 = sy - (float)y0, wy0 = 1.f - wy1, wx1 = sx - (float)x0, wx0 = 1.f - wx1;
-        // four tap weights (fp32 products, rounded once to bf16) -> packed bf16x2 FMAs on 2 channels at a time
-        const __nv_bfloat162 w00 = __float2bfloat162_rn(wy0 * wx0), w01 = __float2bfloat162_rn(wy0 * wx1),
-                             w10 = __float2bfloat162_rn(wy1 * wx0), w11 = __float2bfloat162_rn(wy1 * wx1);
-        const __nv_bfloat16* lb = p.low + (size_t)q.b * h * h * C1;
-        const __nv_bfloat16* p00 = lb + (size_t)(y0 * h + x0) * C1;
-        const __nv_bfloat16* p01 = lb + (size_t)(y0 * h + x1) * C1;
-        const __nv_bfloat16* p10 = lb + (size_t)(y1 * h + x0) * C1;
-        const __nv_bfloat16* p11 = lb + (size_t)(y1 * h + x1) * C1;
-        const __nv_bfloat16* sk = p.in + ((size_t)(q.b * W + (inside ? gy : 0)) * W + (inside ? gx : 0)) * C1;
-        // skip-tensor chunks first (asynchronous), then the bilinear chunks with all their loads in flight
-#pragma unroll
-        for (int c = C1 / 8 + sub; c < NCH; c += TPR)
-          cp_async16(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), sk + (c * 8 - C1), inside);
-        constexpr int NB = (C1 / 8) / TPR;   // bilinear chunks of this thread
-        static_assert(NB >= 1 && NB <= 4 && (C1 / 8) % TPR == 0, "bilinear chunk split");
-        uint4 ta[NB], tb[NB], tc[NB], td[NB];
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const int c = sub + i * TPR;
-          ta[i] = tb[i] = tc[i] = td[i] = make_uint4(0, 0, 0, 0);
-          if (inside) {
-            ta[i] = __ldg(reinterpret_cast<const uint4*>(p00 + c * 8));
-            tb[i] = __ldg(reinterpret_cast<const uint4*>(p01 + c * 8));
-            tc[i] = __ldg(reinterpret_cast<const uint4*>(p10 + c * 8));
-            td[i] = __ldg(reinterpret_cast<const uint4*>(p11 + c * 8));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const int c = sub + i * TPR;
-          const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ta[i]);
-          const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&tb[i]);
-          const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&tc[i]);
-          const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&td[i]);
-          uint4 o;
-          __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            po[j] = __hfma2(w11, pd[j], __hfma2(w10, pc[j], __hfma2(w01, pb[j], __hmul2(w00, pa[j]))));
-          sts128(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), o.x, o.y, o.z, o.w);
-        }
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(bar(B_A1FULL + ab));
-      T(6);
-    };
-
     const int lg = warp & 3, hw = warp >> 2;   // TMEM lane quarter, half (tile or column half)
     auto drain1 = [&](const Patch& q, int u, int c) {
       const int b = u & 1, k = u >> 1;
@@ -382,7 +308,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     };
 
     if (n_mine > 0) {
-      for (int i = 0; i < A1BUFS && i < n_mine; ++i) produce_a1(i);
       int u = 0;
       Patch prev{};
       for (int pi = 0; pi < n_mine; ++pi) {
@@ -393,11 +318,95 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
           // memory, so the depthwise warps never wait for this group to finish an epilogue first
           if (c == 0 && pi > 0) epilogue(prev, pi - 1);
         }
-        if (pi + A1BUFS < n_mine) produce_a1(pi + A1BUFS);
         prev = q;
       }
       epilogue(prev, n_mine - 1);
     }
+  } else if (warp >= 16) {
+    // =========================================== producers: A1[patch] <- global ==================================
+    auto produce_a1 = [&](int pi) {
+      const Patch q = decode(pi);
+      const int ab = pi % A1BUFS, ak = pi / A1BUFS;
+      T(15);
+      mbar_wait(bar(B_A1FREE + ab), (ak & 1) ^ 1);
+      T(5);
+      constexpr int TPR = 1;                        // one producer thread per window pixel ...
+      constexpr int NCH = CIN / 8;                  // 16-byte chunks per pixel
+      constexpr int sub = 0;
+#pragma unroll 1
+      for (int row = tid - 2 * kGroup; row < TILES * 128; row += kProd) {   // ... TILES pixels per thread
+      const int gy = q.GY0 + (row >> 4), gx = q.GX0 + (row & 15);
+      const bool inside = gy >= 0 && gy < W && gx >= 0 && gx < W;
+      const uint32_t a1 = sA1 + ab * C::kA1Buf + (row >> 7) * kTile;
+      const int r = row & 127;
+      if constexpr (!UPCAT) {
+        const __nv_bfloat16* src = p.in + ((size_t)(q.b * W + (inside ? gy : 0)) * W + (inside ? gx : 0)) * CIN;
+#pragma unroll
+        for (int c = sub; c < NCH; c += TPR)
+          cp_async16(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), src + c * 8, inside);
+      } else {
+        constexpr int C1 = CIN / 2;   // channels coming from the upsampled low-res tensor
+        const int h = W / 2;
+        const float sy = (float)(h - 1) / (float)(W - 1) * (float)(inside ? gy : 0);
+        const float sx = (float)(h - 1) / (float)(W - 1) * (float)(inside ? gx : 0);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < h - 1 ? 1 : 0);
+        const float wy1 = sy - (float)y0, wy0 = 1.f - wy1, wx1 = sx - (float)x0, wx0 = 1.f - wx1;
+        // four tap weights (fp32 products, rounded once to bf16) -> packed bf16x2 FMAs on 2 channels at a time
+        const __nv_bfloat162 w00 = __float2bfloat162_rn(wy0 * wx0), w01 = __float2bfloat162_rn(wy0 * wx1),
+                             w10 = __float2bfloat162_rn(wy1 * wx0), w11 = __float2bfloat162_rn(wy1 * wx1);
+        const __nv_bfloat16* lb = p.low + (size_t)q.b * h * h * C1;
+        const __nv_bfloat16* p00 = lb + (size_t)(y0 * h + x0) * C1;
+        const __nv_bfloat16* p01 = lb + (size_t)(y0 * h + x1) * C1;
+        const __nv_bfloat16* p10 = lb + (size_t)(y1 * h + x0) * C1;
+        const __nv_bfloat16* p11 = lb + (size_t)(y1 * h + x1) * C1;
+        const __nv_bfloat16* sk = p.in + ((size_t)(q.b * W + (inside ? gy : 0)) * W + (inside ? gx : 0)) * C1;
+        // skip-tensor chunks first (asynchronous), then the bilinear chunks with all their loads in flight
+#pragma unroll
+        for (int c = C1 / 8 + sub; c < NCH; c += TPR)
+          cp_async16(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), sk + (c * 8 - C1), inside);
+        constexpr int NBIL = C1 / 8;          // bilinear chunks of this pixel, processed 4 at a time
+        constexpr int NB = NBIL < 4 ? NBIL : 4;
+        static_assert(NBIL % NB == 0, "bilinear chunk split");
+#pragma unroll 1
+        for (int c0 = 0; c0 < NBIL; c0 += NB) {
+          uint4 ta[NB], tb[NB], tc[NB], td[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int c = c0 + i;
+            ta[i] = tb[i] = tc[i] = td[i] = make_uint4(0, 0, 0, 0);
+            if (inside) {
+              ta[i] = __ldg(reinterpret_cast<const uint4*>(p00 + c * 8));
+              tb[i] = __ldg(reinterpret_cast<const uint4*>(p01 + c * 8));
+              tc[i] = __ldg(reinterpret_cast<const uint4*>(p10 + c * 8));
+              td[i] = __ldg(reinterpret_cast<const uint4*>(p11 + c * 8));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            const int c = c0 + i;
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ta[i]);
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&tb[i]);
+            const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&tc[i]);
+            const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&td[i]);
+            uint4 o;
+            __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              po[j] = __hfma2(w11, pd[j], __hfma2(w10, pc[j], __hfma2(w01, pb[j], __hmul2(w00, pa[j]))));
+            sts128(a1 + (c >> 3) * TILES * kTile + sw128_off(r, c & 7), o.x, o.y, o.z, o.w);
+          }
+        }
+      }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(bar(B_A1FULL + ab));
+      T(6);
+    };
+
+    for (int pi = 0; pi < n_mine; ++pi) produce_a1(pi);
   } else {
     // =========================================== group A: depthwise 3x3, HID -> A2 ==============================
     // Thread = one 4-channel group (8 B) of one item; 16 groups per pixel, 16 items side by side.
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == kIssuerWarp) tmem_dealloc(tmem, 512);
 }
 
 template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS>

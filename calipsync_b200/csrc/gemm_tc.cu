@@ -5,13 +5,12 @@
 //                            upsample of the low-res tensor for the decoder concat, module/unet.py:90-96).  A stage
 //                            is published kLag k-blocks after it was issued (cp.async.wait_group + proxy fence +
 //                            mbarrier arrive), so several stages of loads stay in flight per thread.
-//                            DW3X3 mode computes the depthwise 3x3 + BN + LeakyReLU of an InvertedResidual on
-//                            the fly (packed bf16x2 FMAs), fusing it into the projection GEMM that follows.
 //   warp  8    B loader      one thread: the weight tile (BN rows) is stored in global memory as the swizzled
 //                            shared-memory image, so a stage is one bulk-async (TMA engine) copy on the same mbarrier.
 //   warp  9    MMA issuer    one thread: 4 x tcgen05.mma (M=128, N=BN, K=16) per k-block into one of two TMEM
 //                            accumulators; tcgen05.commit frees the stage / publishes the accumulator.
-//   warps 10-13 epilogue     drain TMEM (tcgen05.ld 32x32b) and apply the fused epilogue (folded-BN bias,
+//   warps 10-17 epilogue     (two per TMEM lane quarter, half of the columns each; residual rows prefetched)
+//                            drain TMEM (tcgen05.ld 32x32b) and apply the fused epilogue (folded-BN bias,
 //                            LeakyReLU, pre/post residuals, trailing BN) with 16-byte bf16 stores, overlapping the
 //                            main loop of the CTA's next tile.
 // Grid = min(#tiles, #SMs); tiles are walked N-fastest so CTAs that share an A tile run at the same time.
@@ -26,7 +25,8 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kABytes = kBM * 128;   // 16 KiB: 128 rows x 128 B
 constexpr int kProducers = 256;      // 8 producer warps
-constexpr int kThreads = kProducers + 6 * 32;
+constexpr int kEpiWarps = 8;          // two warps per TMEM lane quarter, each owns half of the tile columns
+constexpr int kThreads = kProducers + 2 * 32 + kEpiWarps * 32;
 constexpr int kLag = 2;              // A stages in flight per producer thread before publishing
 
 template <int BN>
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), 128);
+      mbar_init(acc_empty(a), kEpiWarps * 32);
     }
     fence_mbar_init();
   }
@@ -104,14 +104,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
 
   if (warp < 8) {
     // ======================================= A producers =========================================================
-    // PLAIN / CONV3X3 / DW3X3: thread owns chunk (tid & 7) of rows (tid >> 3) + 32 i, i < 4 (a warp copies four
+    // PLAIN / CONV3X3: thread owns chunk (tid & 7) of rows (tid >> 3) + 32 i, i < 4 (a warp copies four
     // full 128 B rows per instruction).  UPCAT: two threads per row (4 chunks each; 4 taps + weights per row).
     int j = 0;           // k-blocks issued by this thread over all tiles (stage = j % S)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / NT) * kBM;
       int conv_pix[4], conv_yx[4];
       RowCoord rc{};
-      if (p.amode == A_CONV3X3 || p.amode == A_DW3X3) {
+      if (p.amode == A_CONV3X3) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int m = m0 + (tid >> 3) + 32 * i;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
               const __nv_bfloat16* src = valid ? p.A + (size_t)m * p.lda + k : p.A;
               cp_async16(a_s + sw128_off(r, c), src, valid);
             }
-          } else if (p.amode == A_CONV3X3) {  // implicit GEMM over the 9 taps of a dense 3x3 conv: k = tap*Cin + ci
+          } else {  // implicit GEMM over the 9 taps of a dense 3x3 conv: k = tap*Cin + ci
             const int tap = k / p.Cin, ci = k - tap * p.Cin;
             const int ky = tap / 3, kx = tap - ky * 3;
 #pragma unroll
@@ -188,57 +188,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
               bool valid = conv_yx[i] >= 0 && k < p.K && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
               const __nv_bfloat16* src = valid ? p.A + (size_t)(conv_pix[i] + ky * p.Win + kx) * p.Cin + ci : p.A;
               cp_async16(a_s + sw128_off(r, c), src, valid);
-            }
-          } else {  // depthwise 3x3 (+ folded BN bias + LeakyReLU) of channels k..k+7, computed here
-            __nv_bfloat162 wt[9][4], wb[4];
-            const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
-            const bool kvalid = k < p.K;
-#pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const float4 w0 = kvalid ? __ldg(reinterpret_cast<const float4*>(p.dw_w + t9 * p.K + k)) : make_float4(0, 0, 0, 0);
-              const float4 w1 = kvalid ? __ldg(reinterpret_cast<const float4*>(p.dw_w + t9 * p.K + k + 4)) : make_float4(0, 0, 0, 0);
-              wt[t9][0] = __floats2bfloat162_rn(w0.x, w0.y);
-              wt[t9][1] = __floats2bfloat162_rn(w0.z, w0.w);
-              wt[t9][2] = __floats2bfloat162_rn(w1.x, w1.y);
-              wt[t9][3] = __floats2bfloat162_rn(w1.z, w1.w);
-            }
-            {
-              const float4 b0 = kvalid ? __ldg(reinterpret_cast<const float4*>(p.dw_b + k)) : make_float4(0, 0, 0, 0);
-              const float4 b1 = kvalid ? __ldg(reinterpret_cast<const float4*>(p.dw_b + k + 4)) : make_float4(0, 0, 0, 0);
-              wb[0] = __floats2bfloat162_rn(b0.x, b0.y);
-              wb[1] = __floats2bfloat162_rn(b0.z, b0.w);
-              wb[2] = __floats2bfloat162_rn(b1.x, b1.y);
-              wb[3] = __floats2bfloat162_rn(b1.z, b1.w);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = (tid >> 3) + 32 * i;
-              __nv_bfloat162 a[4] = {wb[0], wb[1], wb[2], wb[3]};
-              const int iy0 = (conv_yx[i] >> 16) - 64, ix0 = (conv_yx[i] & 0xFFFF) - 64;
-              if (conv_yx[i] >= 0 && kvalid) {
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                  const int iy = iy0 + ky;
-                  if (iy < 0 || iy >= p.Hin) continue;
-#pragma unroll
-                  for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = ix0 + kx;
-                    if (ix < 0 || ix >= p.Win) continue;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.A + (size_t)(conv_pix[i] + ky * p.Win + kx) * p.Cin + k));
-                    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[ky * 3 + kx][q], pv[q], a[q]);
-                  }
-                }
-              }
-              uint32_t o[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                a[q] = __hmax2(a[q], __hmul2(a[q], kslope));
-                o[q] = (conv_yx[i] >= 0 && kvalid) ? *reinterpret_cast<uint32_t*>(&a[q]) : 0u;
-              }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_s + sw128_off(r, c)), "r"(o[0]), "r"(o[1]),
-                           "r"(o[2]), "r"(o[3]));
             }
           }
         }
@@ -294,7 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
     }
   } else {
     // ======================================= epilogue warps ==========================================================
-    const int lg = warp & 3;   // TMEM lane quarter this warp may access
+    const int lg = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ch = (warp - 10) >> 2;         // which half of the tile's columns
+    constexpr int HALF = BN >= 64 ? BN / 2 : BN;   // BN = 32: one chunk, second warp set idles
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
@@ -302,13 +253,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
       mbar_wait(acc_full(ab), (t >> 1) & 1);
       tc_fence_after();
       const int m = m0 + lg * 32 + lane;
+      const bool row_ok = m < p.M;
       const uint32_t trow = tmem + ab * C::kAccCols + ((uint32_t)(lg * 32) << 16);
+      const int cbeg = BN >= 64 ? ch * HALF : 0, cend = BN >= 64 ? cbeg + HALF : (ch == 0 ? BN : 0);
+      // residual rows are prefetched one 32-column chunk ahead so their global-memory latency hides behind the
+      // TMEM load + arithmetic of the current chunk
+      // (a launch uses res_pre or res_post, never both)
+      const __nv_bfloat16* rsrc = p.res_pre ? p.res_pre + (size_t)m * p.ld_rpre : p.res_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
+      uint4 rnext[4];
+      auto fetch_res = [&](int c0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          rnext[g] = (rsrc && row_ok) ? *reinterpret_cast<const uint4*>(rsrc + n0 + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+      };
+      if (cbeg < cend) fetch_res(cbeg);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(trow + c0, acc);
+        uint4 rcur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+        if (c0 + 32 < cend) fetch_res(c0 + 32);
         tmem_ld_wait32(acc);
-        if (m < p.M) {
+        if (row_ok) {
           const int n = n0 + c0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {  // 8 columns per group -> one 16 B store
@@ -319,8 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
             if (p.res_pre) {
-              const uint4 r = *reinterpret_cast<const uint4*>(p.res_pre + (size_t)m * p.ld_rpre + n + 8 * g);
-              const uint32_t* pr = &r.x;
+              const uint32_t* pr = &rcur[g].x;
               const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.rscale + n + 8 * g));
               const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.rscale + n + 8 * g + 4));
               const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -335,8 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
             }
             if (p.res_post) {
-              const uint4 r = *reinterpret_cast<const uint4*>(p.res_post + (size_t)m * p.ld_rpost + n + 8 * g);
-              const uint32_t* pr = &r.x;
+              const uint32_t* pr = &rcur[g].x;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 v[2 * q] += bf16_lo(pr[q]);

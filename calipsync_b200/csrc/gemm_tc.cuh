@@ -6,17 +6,15 @@
 
 namespace casync {
 
-enum AMode : int { A_PLAIN = 0, A_CONV3X3 = 1, A_UPCAT = 2, A_DW3X3 = 3 };
+enum AMode : int { A_PLAIN = 0, A_CONV3X3 = 1, A_UPCAT = 2 };
 
 struct GemmArgs {
   int amode;
-  const __nv_bfloat16* A;   // PLAIN: [M, lda]; CONV3X3 / DW3X3: NHWC [B,Hin,Win,Cin]; UPCAT: low-res NHWC [B,Hin,Win,Cin]
+  const __nv_bfloat16* A;   // PLAIN: [M, lda]; CONV3X3: NHWC [B,Hin,Win,Cin]; UPCAT: low-res NHWC [B,Hin,Win,Cin]
   const __nv_bfloat16* A2;  // UPCAT: skip NHWC [B,Hout,Wout,K-Cin]
   int lda;
   int M, K, N;
   int Hin, Win, Cin, Hout, Wout, stride, pad;
-  const float* dw_w;        // DW3X3: depthwise taps fp32 [9][K] (BN folded) -- A = leaky(dw3x3(A_nhwc) + dw_b), computed by
-  const float* dw_b;        //        the producers on the fly (InvertedResidual conv.3-5 fused into conv.6's GEMM)
   const uint8_t* W;         // packed: k-block kb, row n -> 128 B (64 bf16, SWIZZLE_128B image) at (kb*N+n)*128
   const float* bias;        // [N]
   const float* rscale;      // [N] or null: v += rscale[n] * res_pre[m,n]   (before the activation)

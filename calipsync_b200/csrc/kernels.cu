@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
 // down kDwRows output rows with a sliding 3x3 window in registers (3 new 16 B loads per output at stride 1,
 // 6 at stride 2, instead of 9).  Packed bf16x2 FMAs, the same arithmetic as the fused kernel's depthwise.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDwRows = 8;
+constexpr int kDwRows = 10;
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
@@ -135,36 +135,47 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
       for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[trow * 3 + k][q], pv[q], a[q]);
     }
   };
-  uint4 r0[3], r1[3], r2[3];
-  if (STRIDE == 1) {
-    load_row(oy0 - 1, r0);
-    load_row(oy0, r1);
-  } else {
-    load_row(2 * oy0 - 1, r0);
-  }
-  for (int oy = oy0; oy < oy1; ++oy) {
-    if (STRIDE == 1) {
-      load_row(oy + 1, r2);
-    } else {
-      load_row(2 * oy, r1);
-      load_row(2 * oy + 1, r2);
-    }
+  auto emit = [&](int oy, const uint4* q0, const uint4* q1, const uint4* q2) {
     __nv_bfloat162 a[4] = {wb[0], wb[1], wb[2], wb[3]};
-    taps(a, r0, 0);
-    taps(a, r1, 1);
-    taps(a, r2, 2);
+    taps(a, q0, 0);
+    taps(a, q1, 1);
+    taps(a, q2, 2);
     uint4 o;
     __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int q = 0; q < 4; ++q) po[q] = __hmax2(a[q], __hmul2(a[q], kslope));
     *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
+  };
+  // software pipeline: the loads of the next output row are issued before the current row is computed
+  if (STRIDE == 1) {
+    uint4 r0[3], r1[3], r2[3], rn[3];
+    load_row(oy0 - 1, r0);
+    load_row(oy0, r1);
+    load_row(oy0 + 1, r2);
+    for (int oy = oy0; oy < oy1; ++oy) {
+      load_row(oy + 2, rn);            // prefetch (rows beyond the image / this block's range read as zero or are unused)
+      emit(oy, r0, r1, r2);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (STRIDE == 1) {
+      for (int k = 0; k < 3; ++k) {
         r0[k] = r1[k];
         r1[k] = r2[k];
-      } else {
+        r2[k] = rn[k];
+      }
+    }
+  } else {
+    uint4 r0[3], r1[3], r2[3], n1[3], n2[3];
+    load_row(2 * oy0 - 1, r0);
+    load_row(2 * oy0, r1);
+    load_row(2 * oy0 + 1, r2);
+    for (int oy = oy0; oy < oy1; ++oy) {
+      load_row(2 * oy + 2, n1);
+      load_row(2 * oy + 3, n2);
+      emit(oy, r0, r1, r2);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
         r0[k] = r2[k];
+        r1[k] = n1[k];
+        r2[k] = n2[k];
       }
     }
   }
@@ -205,7 +216,7 @@ struct AttnSmem {
 __global__ void __launch_bounds__(320) attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
                                                         const __nv_bfloat16* __restrict__ k,
                                                         const __nv_bfloat16* __restrict__ v, int ldkv,
-                                                        const __nv_bfloat16* __restrict__ x,
+                                                        const __nv_bfloat16* __restrict__ x, int ldx,
                                                         __nv_bfloat16* __restrict__ out, float gamma) {
   extern __shared__ uint8_t smem_raw[];
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
@@ -289,7 +300,7 @@ __global__ void __launch_bounds__(320) attention_kernel(const __nv_bfloat16* __r
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
       const size_t off = (row0 + i0 + r) * 512 + quarter * 128 + lane * 4;
-      const uint2 xx = __ldg(reinterpret_cast<const uint2*>(x + off));
+      const uint2 xx = __ldg(reinterpret_cast<const uint2*>(x + (row0 + i0 + r) * ldx + quarter * 128 + lane * 4));
       uint2 o;
       o.x = pack_bf16(fmaf(gamma, acc[r][0], bf16_lo(xx.x)), fmaf(gamma, acc[r][1], bf16_hi(xx.x)));
       o.y = pack_bf16(fmaf(gamma, acc[r][2], bf16_lo(xx.y)), fmaf(gamma, acc[r][3], bf16_hi(xx.y)));
@@ -386,8 +397,8 @@ int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStr
 }
 
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
-                     const __nv_bfloat16* x, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st) {
-  attention_kernel<<<dim3(4, batch), 320, sizeof(AttnSmem), st>>>(q, ldq, k, v, ldkv, x, out, gamma);
+                     const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st) {
+  attention_kernel<<<dim3(4, batch), 320, sizeof(AttnSmem), st>>>(q, ldq, k, v, ldkv, x, ldx, out, gamma);
   return (int)cudaGetLastError();
 }
 

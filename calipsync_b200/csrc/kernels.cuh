@@ -29,7 +29,7 @@ int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStr
 // softmax(q k^T) v core of CrossAttention (module/unet.py:209-217) for one attention block:
 //   out[m, c] = gamma * sum_j softmax_j(q[m,:].k[j,:]) v[j,c] + x[m,c]   (per frame: 100 queries x 100 keys)
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
-                     const __nv_bfloat16* x, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st);
+                     const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st);
 // kx = leaky(bn_kx(tx + ox0 + ox1 + ox2 + ox3))  (module/unet.py:329-336), fp32 sum of the bf16 stage tensors
 int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,
                 const __nv_bfloat16* o3, const float* s, const float* t, __nv_bfloat16* kx, long rows,

@@ -131,10 +131,10 @@ const std::vector<Entry>& schema() {
   s.push_back({"attention_blocks|gamma", 4 * 4});
   for (int j = 0; j < 4; ++j) {
     const std::string p = "attention_blocks." + std::to_string(j) + "|";
-    s.push_back({p + "p1_w", packed_bytes(512, 1024)});
-    s.push_back({p + "p1_b", 512 * 4});
-    s.push_back({p + "q_w", packed_bytes(64, 512)});
-    s.push_back({p + "q_b", 64 * 4});
+    // attention_adjust_p_1 (512 rows) stacked with the query projection composed onto it (64 rows):
+    // q = Wq (Wp x + bp) + bq = (Wq Wp) x + (Wq bp + bq), so one GEMM yields [p_1(x) | q]
+    s.push_back({p + "p1q_w", packed_bytes(576, 1024)});
+    s.push_back({p + "p1q_b", 576 * 4});
     s.push_back({p + "b1_w", packed_bytes(1024, 512)});
     s.push_back({p + "b1_b", 1024 * 4});
     s.push_back({p + "b1_rs", 1024 * 4});
@@ -164,8 +164,8 @@ const BufDef kBufs[] = {
     {"x1", 25600, 32},  {"x2", 6400, 64},    {"x3", 1600, 128},  {"x4", 400, 256},   {"cat", 100, 1024},
     {"d1t", 6400, 64},  {"d2t", 1600, 128},  {"d3t", 400, 256},  {"d4t", 100, 512},  {"aud_in", 1024, 32},
     {"a1", 1024, 64},   {"a2", 1024, 128},   {"a3", 256, 256},   {"a4", 256, 256},   {"a5", 100, 512},
-    {"a6", 100, 512},   {"fc1", 100, 1024},  {"tx", 100, 1024},  {"kvall", 100, 2304}, {"p1", 100, 512},
-    {"q", 100, 64},     {"att", 100, 512},   {"ox0", 100, 1024}, {"ox1", 100, 1024}, {"ox2", 100, 1024},
+    {"a6", 100, 512},   {"fc1", 100, 1024},  {"tx", 100, 1024},  {"kvall", 100, 2304}, {"p1q", 100, 576},
+    {"att", 100, 512},   {"ox0", 100, 1024}, {"ox1", 100, 1024}, {"ox2", 100, 1024},
     {"ox3", 100, 1024}, {"kx", 100, 1024},   {"f0", 100, 512},   {"f1", 100, 512},   {"f2", 100, 256},
     {"fuse", 100, 256}, {"t_up1", 400, 128}, {"up1", 400, 128},  {"t_up2", 1600, 64}, {"up2", 1600, 64},
     {"t_up3", 6400, 32}, {"up3", 6400, 32},  {"t_up4", 25600, 32}, {"up4", 25600, 32},
@@ -185,7 +185,6 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
-  bool fuse_dw = false;  // (measured slower than the standalone kernel: off; CASYNC_FUSED_DW=1) depthwise 3x3 inside the projection GEMM (A_DW3X3) for blocks without a fully fused kernel
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
   int phase_dbg_ir = -1;
   template <class T>
@@ -281,24 +280,12 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   CK(launch_gemm(g, st));
   const std::string sn = short_name(d.name);
   prof_mark((sn + ".pw1").c_str(), 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
+  CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
+  prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
   GemmArgs g2{};
-  if (p->fuse_dw) {   // depthwise 3x3 + BN + leaky computed by the projection GEMM's A producers
-    g2.amode = A_DW3X3;
-    g2.A = h1;
-    g2.Hin = g2.Win = H;
-    g2.Cin = hid;
-    g2.Hout = g2.Wout = Ho;
-    g2.stride = d.stride;
-    g2.pad = 1;
-    g2.dw_w = p->w<float>(pre + "wd");
-    g2.dw_b = p->w<float>(pre + "bd");
-  } else {
-    CK(launch_dw3x3(h1, h2, p->w<float>(pre + "wd"), p->w<float>(pre + "bd"), batch, H, H, hid, d.stride, st));
-    prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
-    g2.amode = A_PLAIN;
-    g2.A = h2;
-    g2.lda = hid;
-  }
+  g2.amode = A_PLAIN;
+  g2.A = h2;
+  g2.lda = hid;
   g2.M = batch * Ho * Ho;
   g2.K = hid;
   g2.N = d.cout;
@@ -314,8 +301,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.C = out;
   g2.ldc = ldc;
   CK(launch_gemm(g2, st));
-  prof_mark((sn + (p->fuse_dw ? ".dw+pw2" : ".pw2")).c_str(), 2.0 * g2.M * g2.K * g2.N + (p->fuse_dw ? 18.0 * g2.M * hid : 0.0),
-            2.0 * ((p->fuse_dw ? (double)batch * H * H : (double)g2.M) * g2.K + (double)g2.M * g2.N * (d.res ? 2 : 1)));
+  prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
   return 0;
 }
 
@@ -399,12 +385,10 @@ int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const 
   const bf16* ox = w["tx"];
   for (int j = 0; j < 4; ++j) {
     const std::string pre = "attention_blocks." + std::to_string(j) + "|";
-    if ((e = run_dense(p, (pre + "p1_w").c_str(), (pre + "p1_b").c_str(), ox, 1024, M, 1024, 512, w["p1"], 512, 0,
+    if ((e = run_dense(p, (pre + "p1q_w").c_str(), (pre + "p1q_b").c_str(), ox, 1024, M, 1024, 576, w["p1q"], 576, 0,
                        nullptr, 0, nullptr, st))) return e;
-    if ((e = run_dense(p, (pre + "q_w").c_str(), (pre + "q_b").c_str(), w["p1"], 512, M, 512, 64, w["q"], 64, 0, nullptr,
-                       0, nullptr, st))) return e;
-    CK(launch_attention(w["q"], 64, w["kvall"] + j * 576, w["kvall"] + j * 576 + 64, 2304, w["p1"], w["att"],
-                        p->gamma[j], batch, st));
+    CK(launch_attention(w["p1q"] + 512, 576, w["kvall"] + j * 576, w["kvall"] + j * 576 + 64, 2304, w["p1q"], 576,
+                        w["att"], p->gamma[j], batch, st));
     prof_mark(("attn" + std::to_string(j) + ".core").c_str(), 2.0 * batch * (100.0 * 100 * 64 + 100.0 * 100 * 512),
               2.0 * batch * 100 * (64 + 576 + 512 + 512));
     if ((e = run_dense(p, (pre + "b1_w").c_str(), (pre + "b1_b").c_str(), w["att"], 512, M, 512, 1024, w[oxn[j]], 1024, 1,
@@ -511,7 +495,6 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
     p->phase_dbg_ir = atoi(c);
     if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
   }
-  if (const char* c = getenv("CASYNC_FUSED_DW")) p->fuse_dw = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_CHUNK")) {
     int v = atoi(c);
@@ -553,13 +536,13 @@ size_t casync_stage_scratch_bytes(const casync_plan* plan, int batch) { return c
 
 int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
   if (!plan || batch <= 0) return 0;
-  int64_t per_chunk = 1 /*inc*/ + 1 /*audio prep*/ + 2 /*conv3, conv5*/ + 3 /*fc1, fc2, kv*/ + 4 * 4 /*attention*/ + 1 + 1;
+  int64_t per_chunk = 1 /*inc*/ + 1 /*audio prep*/ + 2 /*conv3, conv5*/ + 3 /*fc1, fc2, kv*/ + 4 * 3 /*attention*/ + 1 + 1;
   for (int i = 1; i < kNumIr; ++i) {
     const IrDef& d = kIr[i];
     const bool up = i >= IR_UP && !((i - IR_UP) & 1);
     const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) &&
                        fused_ir_supported(d.cin, d.cout, d.stride, up, d.res);
-    per_chunk += fused ? 1 : (plan->fuse_dw ? 2 : 3);
+    per_chunk += fused ? 1 : 3;
   }
   return per_chunk * ((batch + plan->chunk - 1) / plan->chunk);
 }

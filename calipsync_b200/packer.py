@@ -123,12 +123,15 @@ def build_entries(sd):
                 val = _f32(torch.cat([sd["attention_blocks.%d.cross_attention.gamma" % j].double().reshape(1)
                                       for j in range(4)]))
         elif prefix.startswith("attention_blocks."):
-            if part.startswith("p1"):
-                m = prefix + ".attention_adjust_p_1"
-                val = pack_gemm_weight(sd[m + ".weight"].double().flatten(1)) if part == "p1_w" else _f32(sd[m + ".bias"])
-            elif part.startswith("q"):
-                m = prefix + ".cross_attention.query_conv"
-                val = pack_gemm_weight(sd[m + ".weight"].double().flatten(1)) if part == "q_w" else _f32(sd[m + ".bias"])
+            if part.startswith("p1q"):
+                # [attention_adjust_p_1 ; query_conv o attention_adjust_p_1]  (module/unet.py:264, 209): one GEMM
+                # emits p_1(x) and q = Wq(Wp x + bp) + bq
+                wp = sd[prefix + ".attention_adjust_p_1.weight"].double().flatten(1)
+                bp = sd[prefix + ".attention_adjust_p_1.bias"].double()
+                wq = sd[prefix + ".cross_attention.query_conv.weight"].double().flatten(1)
+                bq = sd[prefix + ".cross_attention.query_conv.bias"].double()
+                val = pack_gemm_weight(torch.cat([wp, wq @ wp], 0)) if part == "p1q_w" else \
+                    _f32(torch.cat([bp, wq @ bp + bq], 0))
             else:  # ox = leaky(bn(b_1(.) + tx))  (module/unet.py:266-269): the BN scale also multiplies tx
                 m = prefix + ".attention_adjust_b_1"
                 s, t = _bn_fold(sd, prefix + ".bn")

@@ -81,8 +81,8 @@ class PackedNet:
         ox, oxs = tx, []
         for j in range(4):
             p = "attention_blocks.%d|" % j
-            p1 = self.r(self.pw(ox, p + "p1_w", p + "p1_b", 512, 1024))
-            q = self.r(self.pw(p1, p + "q_w", p + "q_b", 64, 512)).reshape(B, 64, 100)
+            p1q = self.r(self.pw(ox, p + "p1q_w", p + "p1q_b", 576, 1024))
+            p1, q = p1q[:, :512], p1q[:, 512:].reshape(B, 64, 100)
             k = kv[:, j * 576: j * 576 + 64].reshape(B, 64, 100)
             v = kv[:, j * 576 + 64: (j + 1) * 576].reshape(B, 512, 100)
             attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), -1)
