@@ -5,7 +5,41 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
+#ifndef CASYNC_MBAR_HINT_NS
+#define CASYNC_MBAR_HINT_NS 1000000
+#endif
+
 namespace casync {
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it calls
+// pdl_launch_dependents() first (so the NEXT launch may become resident as SMs drain and run its prologue --
+// barrier init, TMEM allocation, weight fetches) and pdl_wait() before it touches any activation buffer
+// (blocks until the previous kernel has completed and its writes are visible).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool& pdl_enabled() {
+  static bool on = true;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 constexpr float kLeaky = 0.01f;  // nn.LeakyReLU() default slope (module/unet.py:20)
 
@@ -28,10 +62,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): the warp sleeps in
+      "selp.u32 %0, 1, 0, p;\n\t}"                                      // hardware instead of spinning through issue slots
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"((uint32_t)CASYNC_MBAR_HINT_NS)
       : "memory");
   return ok != 0;
 }

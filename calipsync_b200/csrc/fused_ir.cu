@@ -23,6 +23,16 @@
 
 #include <cuda_bf16.h>
 
+#ifndef FUSED_OPT_DRAIN2
+#define FUSED_OPT_DRAIN2 0
+#endif
+#ifndef FUSED_OPT_RESPF
+#define FUSED_OPT_RESPF 1
+#endif
+#ifndef FUSED_OPT_DWPF
+#define FUSED_OPT_DWPF 1
+#endif
+
 namespace casync {
 
 namespace {
@@ -97,6 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
   auto bar = [&](int i) { return sBAR + 8u * i; };
   const uint32_t tmem_slot = sBAR + 8u * B_COUNT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     mbar_init(bar(B_W), 1);
@@ -132,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   const uint32_t tD2 = tmem + C::kTmemD2;
   mbar_wait(bar(B_W), 0);
+  pdl_wait();   // weights (constant) are already on their way; activations only after the previous kernel is done
 
   const int W = p.W, Wo = W / STRIDE;
   const int PDX = (Wo + TOW - 1) / TOW, PDY = (Wo + TOH - 1) / TOH;
@@ -230,11 +242,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
       const bool inside = gy >= 0 && gy < W && gx >= 0 && gx < W;
       const uint32_t hid = sHID + b * C::kHidBuf + tile * kTile + (row & 127) * 128;
       const uint32_t r7 = row & 7;
-#pragma unroll
-      for (int cc = 0; cc < NCOL; cc += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem + (b * TILES + tile) * 64 + col0 + cc + ((uint32_t)(lg * 32) << 16), acc);
-        tmem_ld_wait32(acc);
+      const uint32_t tsrc = tmem + (b * TILES + tile) * 64 + col0 + ((uint32_t)(lg * 32) << 16);
+      uint32_t accA[32], accB[32];
+      tmem_ld32(tsrc, accA);
+      tmem_ld_wait32(accA);
+#if FUSED_OPT_DRAIN2
+      if constexpr (NCOL == 64) tmem_ld32(tsrc + 32, accB);   // in flight while the first half is converted
+#endif
+      auto convert = [&](const uint32_t* acc, int cc) {
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const int col = col0 + cc + g8 * 8;
@@ -252,6 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
           }
           sts128(hid + ((((uint32_t)col >> 3) ^ r7) << 4), o[0], o[1], o[2], o[3]);
         }
+      };
+      convert(accA, 0);
+      if constexpr (NCOL == 64) {
+#if !FUSED_OPT_DRAIN2
+        tmem_ld32(tsrc + 32, accB);
+#endif
+        tmem_ld_wait32(accB);
+        convert(accB, 32);
       }
       tc_fence_before();
       mbar_arrive(bar(B_D1FREE + b));
@@ -261,9 +284,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
 
     auto epilogue = [&](const Patch& q, int pi) {
       T(15);
-      mbar_wait(bar(B_D2FULL), pi & 1);
-      T(10);
-      tc_fence_after();
       constexpr int NCOL = A2T == 2 ? COUT : COUT / 2;
       const int tile = A2T == 2 ? hw : 0, col0 = A2T == 2 ? 0 : hw * (COUT / 2);
       const int op = tile * 128 + lg * 32 + lane;
@@ -271,6 +291,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
       const int gy = q.OY0 + oy, gx = q.OX0 + ox;
       const bool valid = op < NOUT && gy < Wo && gx < Wo;
       const size_t opix = (size_t)(q.b * Wo + (valid ? gy : 0)) * Wo + (valid ? gx : 0);
+      // the skip rows (block input at the output pixel) are fetched BEFORE waiting for the accumulator, so their
+      // global-memory latency overlaps the depthwise / second GEMM of this patch
+      uint4 rr[RES ? NCOL / 8 : 1];
+#if FUSED_OPT_RESPF
+      if constexpr (RES) {
+#pragma unroll
+        for (int i = 0; i < NCOL / 8; ++i)
+          rr[i] = valid ? __ldg(reinterpret_cast<const uint4*>(p.in + opix * CIN + col0 + i * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#endif
+      mbar_wait(bar(B_D2FULL), pi & 1);
+#if !FUSED_OPT_RESPF
+      if constexpr (RES) {
+#pragma unroll
+        for (int i = 0; i < NCOL / 8; ++i)
+          rr[i] = valid ? __ldg(reinterpret_cast<const uint4*>(p.in + opix * CIN + col0 + i * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#endif
+      T(10);
+      tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < NCOL; cc += 16) {
         uint32_t acc[16];
@@ -289,8 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
               v[j] = fmaxf(v[j], kLeaky * v[j]);
             }
             if constexpr (RES) {   // stride 1, CIN == COUT: skip = the block input at the same pixel
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.in + opix * CIN + col));
-              const uint32_t* pr = &rr.x;
+              const uint32_t* pr = &rr[(cc >> 3) + g8].x;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 v[2 * j] += bf16_lo(pr[j]);
@@ -461,17 +500,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
             uint32_t cb[4];
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) cb[kx] = hid + oy0 * 2048 + (ox + kx) * 128 + ((chunk ^ ((ox + kx) & 7)) << 4);
-            uint2 r0[4], r1[4], r2[4];
+            uint2 r0[4], r1[4], r2[4], rn[4];
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) {
               r0[kx] = lds64(cb[kx]);
               r1[kx] = lds64(cb[kx] + 2048);
+              r2[kx] = lds64(cb[kx] + 2 * 2048);
             }
             int op = oy0 * 14 + ox;
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
+              // the window row of the NEXT output row is requested before this row's 36 FMAs, so the shared-memory
+              // latency hides behind them
+#if FUSED_OPT_DWPF
+              if (i + 1 < RB) {
 #pragma unroll
-              for (int kx = 0; kx < 4; ++kx) r2[kx] = lds64(cb[kx] + (i + 2) * 2048);
+                for (int kx = 0; kx < 4; ++kx) rn[kx] = lds64(cb[kx] + (i + 3) * 2048);
+              }
+#endif
               __nv_bfloat162 a[2] = {wbias[0], wbias[1]}, e[2] = {wbias[0], wbias[1]};
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
@@ -485,10 +531,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
               finish(a, a2 + op * 128 + ((chunk ^ (op & 7)) << 4));   // A2 tiles are contiguous: row op
               finish(e, a2 + (op + 1) * 128 + ((chunk ^ ((op + 1) & 7)) << 4));
               op += 14;
+#if !FUSED_OPT_DWPF
+              if (i + 1 < RB) {
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) rn[kx] = lds64(cb[kx] + (i + 3) * 2048);
+              }
+#endif
 #pragma unroll
               for (int kx = 0; kx < 4; ++kx) {
                 r0[kx] = r1[kx];
                 r1[kx] = r2[kx];
+                r2[kx] = rn[kx];
               }
             }
           }
@@ -533,8 +586,7 @@ int launch_t(const FusedArgs& a, cudaStream_t st) {
   const int Wo = a.W / STRIDE;
   const int NP = a.batch * ((Wo + C::TOW - 1) / C::TOW) * ((Wo + C::TOH - 1) / C::TOH);
   const int grid = NP < a.num_sms ? NP : a.num_sms;
-  kfn<<<grid, kThreads, C::kSmem, st>>>(a);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(kfn, dim3(grid), dim3(kThreads), C::kSmem, st, a);
 }
 
 }  // namespace

@@ -1,7 +1,9 @@
 // tcgen05 GEMM kernel (sm_100a), persistent and warp-specialised.  C[M,N] = epilogue(A[M,K] . W[N,K]^T).
 //
-//   warps 0-7  A producers   256 threads fill the A stage (128 rows x 64 bf16, SWIZZLE_128B): cp.async 16 B chunks
-//                            for plain rows and implicit-GEMM 3x3 taps, or values computed on the fly (bilinear x2
+//   warps 0-7  A producers   plain row-major A: ONE thread issues a 2-D TMA tensor copy per stage (box 64 x 128,
+//                            SWIZZLE_128B, rows beyond M zero-filled by the TMA unit) -- the other producer threads
+//                            idle.  Gathered A: 256 threads fill the A stage (128 rows x 64 bf16, SWIZZLE_128B) with
+//                            cp.async 16 B chunks (implicit-GEMM 3x3 taps), or values computed on the fly (bilinear x2
 //                            upsample of the low-res tensor for the decoder concat, module/unet.py:90-96).  A stage
 //                            is published kLag k-blocks after it was issued (cp.async.wait_group + proxy fence +
 //                            mbarrier arrive), so several stages of loads stay in flight per thread.
@@ -16,7 +18,10 @@
 // Grid = min(#tiles, #SMs); tiles are walked N-fastest so CTAs that share an A tile run at the same time.
 #include "gemm_tc.cuh"
 
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <cstring>
 
 namespace casync {
 
@@ -33,7 +38,7 @@ template <int BN>
 struct Cfg {
   static constexpr int kStage = kABytes + BN * 128;
   static constexpr int S = (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;   // 256:4  128:6  64:8  32:8
-  static constexpr int kSmem = S * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = S * kStage + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue vectors*/;
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
 };
@@ -63,8 +68,15 @@ __device__ __forceinline__ uint4 lerp8(const uint4& a, const uint4& b, const uin
   return o;
 }
 
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
   using C = Cfg<BN>;
   constexpr int S = C::S;
   extern __shared__ uint8_t smem_raw[];
@@ -77,13 +89,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   const int KB = (p.K + 63) >> 6;
   const int NT = p.N / BN, MT = (p.M + kBM - 1) / kBM;
   const int n_tiles = NT * MT;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full(s), kProducers + 1);
+      mbar_init(full(s), p.amode == A_PLAIN ? 2 : kProducers + 1);   // PLAIN: the TMA thread + the B loader
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -101,9 +114,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  // weights are constant: the B loader (and the MMA issuer behind it) start at once; every role that reads or
+  // writes an activation buffer first waits for the previous kernel of the stream
+  if (warp < 8 || warp >= 10) pdl_wait();
 
-  if (warp < 8) {
-    // ======================================= A producers =========================================================
+  if (warp < 8 && p.amode == A_PLAIN) {
+    // ======================================= A via TMA (one thread) ==================================================
+    if (tid == 0) {
+      int j = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / NT) * kBM;
+        for (int kb = 0; kb < KB; ++kb, ++j) {
+          const int s = j % S;
+          mbar_wait(empty(s), ((j / S) & 1) ^ 1);
+          mbar_arrive_expect_tx(full(s), kABytes);
+          tma_load_2d(base + s * C::kStage, &tmA, kb * 64, m0, full(s));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ======================================= A producers (gathered operand) ========================================
     // PLAIN / CONV3X3: thread owns chunk (tid & 7) of rows (tid >> 3) + 32 i, i < 4 (a warp copies four
     // full 128 B rows per instruction).  UPCAT: two threads per row (4 chunks each; 4 taps + weights per row).
     int j = 0;           // k-blocks issued by this thread over all tiles (stage = j % S)
@@ -245,11 +275,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
     // ======================================= epilogue warps ==========================================================
     const int lg = warp & 3;                 // TMEM lane quarter this warp may access
     const int ch = (warp - 10) >> 2;         // which half of the tile's columns
+    // per-tile epilogue vectors (bias, residual scale, trailing BN) are staged in shared memory while the tile's
+    // main loop runs, double-buffered across tiles: [buffer][bias | rscale | post_scale | post_shift][256]
+    float* const evec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+    const int et = tid - (kProducers + 64);
     constexpr int HALF = BN >= 64 ? BN / 2 : BN;   // BN = 32: one chunk, second warp set idles
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
       const int n0 = (tile % NT) * BN, m0 = (tile / NT) * kBM;
+      float* const ev = evec + (t & 1) * 1024;
+      if (et < BN) {
+        ev[et] = __ldg(p.bias + n0 + et);
+        if (p.res_pre) ev[256 + et] = __ldg(p.rscale + n0 + et);
+        if (p.post_scale) {
+          ev[512 + et] = __ldg(p.post_scale + n0 + et);
+          ev[768 + et] = __ldg(p.post_shift + n0 + et);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       mbar_wait(acc_full(ab), (t >> 1) & 1);
       tc_fence_after();
       const int m = m0 + lg * 32 + lane;
@@ -281,15 +325,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
 #pragma unroll
           for (int g = 0; g < 4; ++g) {  // 8 columns per group -> one 16 B store
             float v[8];
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * g));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * g + 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
             if (p.res_pre) {
               const uint32_t* pr = &rcur[g].x;
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.rscale + n + 8 * g));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.rscale + n + 8 * g + 4));
+              const float4 s0 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g + 4);
               const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -310,10 +354,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
               }
             }
             if (p.post_scale) {
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.post_scale + n + 8 * g));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.post_scale + n + 8 * g + 4));
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.post_shift + n + 8 * g));
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.post_shift + n + 8 * g + 4));
+              const float4 s0 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g);
+              const float4 t1 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g + 4);
               const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
               const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
@@ -343,12 +387,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p) 
 
 int g_num_sms = 148;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
 template <int BN>
 int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   const int tiles = (a.N / BN) * ((a.M + kBM - 1) / kBM);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, stream>>>(a);
-  return (int)cudaGetLastError();
+  const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
+  const int grid = tiles < cap ? tiles : cap;
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if (a.amode == A_PLAIN) {
+    // A[M, K] bf16 row-major with pitch lda: box = 64 columns (128 B, one swizzle span) x 128 rows
+    if (!g_encode || (a.lda & 7) || ((uintptr_t)a.A & 15)) return (int)cudaErrorInvalidValue;
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    if (g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorInvalidValue;
+  }
+  return (int)launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, stream, a, tm);
 }
 
 template <int BN>
@@ -357,10 +420,10 @@ int set_attr() {
 }
 
 // work-per-SM proxy: waves of tiles x (per-tile cost ~ A bytes + B bytes per k-block, the L2->smem traffic)
-double tile_cost(long mt, int N, int bn) {
+double tile_cost(long mt, int N, int bn, int cap) {
   if (N % bn) return 1e30;
   const long tiles = mt * (N / bn);
-  const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+  const long waves = (tiles + cap - 1) / cap;
   return (double)waves * (kABytes + bn * 128 + 6000 /*fixed per-k-block/tile overhead*/);
 }
 
@@ -372,6 +435,14 @@ int gemm_init() {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     g_num_sms = sms;
   int e = 0;
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !fn)
+      return (int)cudaErrorNotSupported;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
   e |= set_attr<32>();
   e |= set_attr<64>();
   e |= set_attr<128>();
@@ -383,10 +454,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
   if (a.N % 32 != 0 || a.K % 8 != 0) return (int)cudaErrorInvalidValue;
   const long mt = (a.M + kBM - 1) / kBM;
+  const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   int best = 32;
-  double bc = tile_cost(mt, a.N, 32);
+  double bc = tile_cost(mt, a.N, 32, cap);
   for (int bn : {64, 128, 256}) {
-    const double c = tile_cost(mt, a.N, bn);
+    const double c = tile_cost(mt, a.N, bn, cap);
     if (c <= bc) {
       bc = c;
       best = bn;

@@ -27,6 +27,7 @@ struct GemmArgs {
   const float* post_shift;
   __nv_bfloat16* C;
   int ldc;
+  int max_ctas;             // 0: one CTA per SM; >0: cap (two branches of the forward sharing the GPU on two streams)
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);  // returns 0 or cudaError

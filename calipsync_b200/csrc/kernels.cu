@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
   __shared__ float s_in[6][kIncHalo];
   __shared__ float s_h[12][kIncHalo];
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int x0 = blockIdx.x * kIncTW, y0 = blockIdx.y * kIncTH, b = blockIdx.z;
   const float* xb = x + (size_t)b * 6 * 25600;
   for (int idx = tid; idx < 6 * kIncHalo; idx += 256) {
@@ -79,24 +81,28 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 (+ folded BN bias + LeakyReLU): thread = 8 channels (16 B) of one output column, walking
-// down kDwRows output rows with a sliding 3x3 window in registers (3 new 16 B loads per output at stride 1,
-// 6 at stride 2, instead of 9).  Packed bf16x2 FMAs, the same arithmetic as the fused kernel's depthwise.
+// depthwise 3x3 (+ folded BN bias + LeakyReLU) for the blocks that are not fully fused.  CTA = (64-channel
+// slice, band of output rows, frame).  The input band with a zero border -- (rows*S+2) x (W+2) pixels x 128 B --
+// is fetched with cp.async, every load of the CTA in flight at once (the old register-window version had
+// ~16 KB in flight per SM and ran at 1.3 TB/s); then unit = (output pixel, 16-byte channel chunk): nine
+// conflict-free LDS.128, packed bf16x2 FMAs (same arithmetic as the fused kernel's depthwise), one 16 B store.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDwRows = 10;
+constexpr int kDwSmemMax = 56 * 1024;
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
                                                     __nv_bfloat16* __restrict__ out, const float* __restrict__ wd,
                                                     const float* __restrict__ bd, int H, int W, int C, int Ho,
-                                                    int Wo) {
-  const int c8n = C >> 3;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const int c8 = idx % c8n, ox = idx / c8n;
-  if (ox >= Wo) return;
-  const int c = c8 * 8, b = blockIdx.z;
-  const int oy0 = blockIdx.y * kDwRows;
-  const int oy1 = oy0 + kDwRows < Ho ? oy0 + kDwRows : Ho;
+                                                    int Wo, int BR) {
+  extern __shared__ uint4 dw_tile[];   // [rows_in][W + 2][8 chunks of 8 channels]
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, chunk = tid & 7;
+  const int c0 = blockIdx.x * 64, oy0 = blockIdx.y * BR, b = blockIdx.z;
+  const int rows_out = BR < Ho - oy0 ? BR : Ho - oy0;
+  const int rows_in = (rows_out - 1) * STRIDE + 3, TW = W + 2;
+  const int iy0 = oy0 * STRIDE - 1;
+  // taps / bias of this thread's 8 channels (constants: fetched before waiting for the previous kernel)
+  const int c = c0 + chunk * 8;
   __nv_bfloat162 wt[9][4], wb[4];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
@@ -116,68 +122,39 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
     wb[3] = __floats2bfloat162_rn(b1.z, b1.w);
   }
   const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
+  pdl_wait();   // the hidden tensor is the previous kernel's output
   const __nv_bfloat16* ib = in + (size_t)b * H * W * C + c;
-  const int ix0 = ox * STRIDE - 1;
-  auto load_row = [&](int iy, uint4* r) {   // three horizontal taps of input row iy (zero outside the image)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int ix = ix0 + k;
-      r[k] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                 ? __ldg(reinterpret_cast<const uint4*>(ib + ((size_t)iy * W + ix) * C))
-                 : make_uint4(0, 0, 0, 0);
-    }
-  };
-  auto taps = [&](__nv_bfloat162* a, const uint4* r, int trow) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&r[k]);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[trow * 3 + k][q], pv[q], a[q]);
-    }
-  };
-  auto emit = [&](int oy, const uint4* q0, const uint4* q1, const uint4* q2) {
+  const uint32_t tile_s = smem_u32(dw_tile);
+  const int npx = rows_in * TW;
+  for (int px = tid >> 3; px < npx; px += 32) {      // 256 % 8 == 0: a thread always copies its own chunk column
+    const int ty = px / TW, tx = px - ty * TW;
+    const int iy = iy0 + ty, ix = tx - 1;
+    const bool valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    cp_async16(tile_s + (uint32_t)(px * 8 + chunk) * 16u, valid ? ib + ((size_t)iy * W + ix) * C : ib, valid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int nunits = rows_out * Wo;
+  __nv_bfloat16* ob = out + ((size_t)b * Ho + oy0) * Wo * C + c;
+  for (int p = tid >> 3; p < nunits; p += 32) {
+    const int oy = p / Wo, ox = p - oy * Wo;
+    const uint4* t0 = dw_tile + ((oy * STRIDE) * TW + ox * STRIDE) * 8 + chunk;
     __nv_bfloat162 a[4] = {wb[0], wb[1], wb[2], wb[3]};
-    taps(a, q0, 0);
-    taps(a, q1, 1);
-    taps(a, q2, 2);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint4 v = t0[(ky * TW + kx) * 8];
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[ky * 3 + kx][q], pv[q], a[q]);
+      }
     uint4 o;
     __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int q = 0; q < 4; ++q) po[q] = __hmax2(a[q], __hmul2(a[q], kslope));
-    *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C + c) = o;
-  };
-  // software pipeline: the loads of the next output row are issued before the current row is computed
-  if (STRIDE == 1) {
-    uint4 r0[3], r1[3], r2[3], rn[3];
-    load_row(oy0 - 1, r0);
-    load_row(oy0, r1);
-    load_row(oy0 + 1, r2);
-    for (int oy = oy0; oy < oy1; ++oy) {
-      load_row(oy + 2, rn);            // prefetch (rows beyond the image / this block's range read as zero or are unused)
-      emit(oy, r0, r1, r2);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        r0[k] = r1[k];
-        r1[k] = r2[k];
-        r2[k] = rn[k];
-      }
-    }
-  } else {
-    uint4 r0[3], r1[3], r2[3], n1[3], n2[3];
-    load_row(2 * oy0 - 1, r0);
-    load_row(2 * oy0, r1);
-    load_row(2 * oy0 + 1, r2);
-    for (int oy = oy0; oy < oy1; ++oy) {
-      load_row(2 * oy + 2, n1);
-      load_row(2 * oy + 3, n2);
-      emit(oy, r0, r1, r2);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        r0[k] = r2[k];
-        r1[k] = n1[k];
-        r2[k] = n2[k];
-      }
-    }
+    *reinterpret_cast<uint4*>(ob + (size_t)p * C) = o;
   }
 }
 
@@ -187,6 +164,8 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) audio_prep_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ out,
                                                          long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const long b = p >> 10, r = p & 1023;
@@ -221,6 +200,8 @@ __global__ void __launch_bounds__(320) attention_kernel(const __nv_bfloat16* __r
   extern __shared__ uint8_t smem_raw[];
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const int quarter = blockIdx.x;
   const size_t row0 = (size_t)blockIdx.y * kT;
   for (int idx = tid; idx < kT * 32; idx += 320) {
@@ -315,6 +296,8 @@ __global__ void __launch_bounds__(256) sum5_kernel(const uint4* __restrict__ tx,
                                                    const uint4* __restrict__ o1, const uint4* __restrict__ o2,
                                                    const uint4* __restrict__ o3, const float* __restrict__ s,
                                                    const float* __restrict__ t, uint4* __restrict__ kx, long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const int c = (int)(i & 127) * 8;  // 1024 channels = 128 chunks of 8
@@ -336,6 +319,8 @@ __global__ void __launch_bounds__(256) sum5_kernel(const uint4* __restrict__ tx,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) outc_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out,
                                                    const __grid_constant__ OutcParams w, long npix, int u8_hwc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const uint4* src = reinterpret_cast<const uint4*>(x + p * 32);
@@ -371,51 +356,58 @@ __global__ void __launch_bounds__(256) outc_kernel(const __nv_bfloat16* __restri
 }  // namespace
 
 int kernels_init() {
-  return (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(AttnSmem));
+  int e = (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
+  return e;
 }
 
 int launch_inc(const float* x, __nv_bfloat16* out, const IncParams& w, int batch, cudaStream_t st) {
   dim3 grid(160 / kIncTW, 160 / kIncTH, batch);
-  inc_kernel<<<grid, 256, 0, st>>>(x, out, w);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(inc_kernel, grid, dim3(256), 0, st, x, out, w);
 }
 
 int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
                  int W, int C, int stride, cudaStream_t st) {
+  if (C % 64 != 0 || (stride != 1 && stride != 2)) return (int)cudaErrorInvalidValue;
   const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
-  const dim3 grid((unsigned)((Wo * (C / 8) + 255) / 256), (unsigned)((Ho + kDwRows - 1) / kDwRows), (unsigned)batch);
-  if (stride == 2) dw3x3_kernel<2><<<grid, 256, 0, st>>>(in, out, wd, bd, H, W, C, Ho, Wo);
-  else dw3x3_kernel<1><<<grid, 256, 0, st>>>(in, out, wd, bd, H, W, C, Ho, Wo);
-  return (int)cudaGetLastError();
+  // rows per band: the input band (BR*stride + 2 rows of (W+2) pixels x 128 B) must fit the smem budget
+  const int row_bytes = (W + 2) * 128;
+  int BR = ((kDwSmemMax - 1024) / row_bytes - 3) / stride + 1;
+  if (BR < 1) return (int)cudaErrorInvalidValue;
+  if (BR > Ho) BR = Ho;
+  const int bands = (Ho + BR - 1) / BR;
+  BR = (Ho + bands - 1) / bands;   // balance the bands
+  const size_t smem = (size_t)((BR - 1) * stride + 3) * row_bytes;
+  const dim3 grid((unsigned)(C / 64), (unsigned)bands, (unsigned)batch);
+  if (stride == 2) return (int)launch_pdl(dw3x3_kernel<2>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
+  return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
 }
 
 int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st) {
   const long npix = (long)batch * 1024;
-  audio_prep_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(audio, out, npix);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(audio_prep_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, audio, out, npix);
 }
 
 int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
                      const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st) {
-  attention_kernel<<<dim3(4, batch), 320, sizeof(AttnSmem), st>>>(q, ldq, k, v, ldkv, x, ldx, out, gamma);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(attention_kernel, dim3(4, batch), dim3(320), sizeof(AttnSmem), st, q, ldq, k, v, ldkv, x, ldx,
+                         out, gamma);
 }
 
 int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,
                 const __nv_bfloat16* o3, const float* s, const float* t, __nv_bfloat16* kx, long rows,
                 cudaStream_t st) {
   const long n8 = rows * 128;
-  sum5_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const uint4*>(tx), reinterpret_cast<const uint4*>(o0), reinterpret_cast<const uint4*>(o1),
-      reinterpret_cast<const uint4*>(o2), reinterpret_cast<const uint4*>(o3), s, t, reinterpret_cast<uint4*>(kx), n8);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(sum5_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, st,
+                         reinterpret_cast<const uint4*>(tx), reinterpret_cast<const uint4*>(o0),
+                         reinterpret_cast<const uint4*>(o1), reinterpret_cast<const uint4*>(o2),
+                         reinterpret_cast<const uint4*>(o3), s, t, reinterpret_cast<uint4*>(kx), n8);
 }
 
 int launch_outc(const __nv_bfloat16* x, void* out, const OutcParams& w, int batch, int u8_hwc, cudaStream_t st) {
   const long npix = (long)batch * 25600;
-  outc_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(x, out, w, npix, u8_hwc);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(outc_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, x, out, w, npix, u8_hwc);
 }
 
 }  // namespace casync

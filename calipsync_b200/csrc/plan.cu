@@ -34,6 +34,7 @@ struct Prof {
   std::vector<casync_launch_record> recs;
 };
 thread_local Prof* g_prof = nullptr;
+thread_local int g_cap = 0;   // CTA cap of persistent kernels while two branches of the forward share the GPU
 void prof_mark(const char* label, double flops, double bytes) {
   if (!g_prof) return;
   casync_launch_record r{};
@@ -170,6 +171,7 @@ const BufDef kBufs[] = {
     {"fuse", 100, 256}, {"t_up1", 400, 128}, {"up1", 400, 128},  {"t_up2", 1600, 64}, {"up2", 1600, 64},
     {"t_up3", 6400, 32}, {"up3", 6400, 32},  {"t_up4", 25600, 32}, {"up4", 25600, 32},
     {"h1", 25600, 128}, {"h2", 25600, 128},
+    {"ah1", 256, 512},  {"ah2", 256, 512},   // hidden tensors of the audio branch (runs on its own stream)
 };
 constexpr int kNumBufs = sizeof(kBufs) / sizeof(kBufs[0]);
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -185,6 +187,10 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
+  bool overlap = false;             // CASYNC_OVERLAP=1: audio encoder on a side stream next to the low-resolution face
+                                    // encoder (measured: no gain at batch 64 -- both branches are wave-bound, not idle)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
   int phase_dbg_ir = -1;
   template <class T>
@@ -243,7 +249,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     f.b2 = p->w<float>(pre + "b2");
     f.W = H;
     f.batch = batch;
-    f.num_sms = p->num_sms;
+    f.num_sms = g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms;
     f.cin = d.cin;
     f.cout = d.cout;
     f.stride = d.stride;
@@ -265,6 +271,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g.leaky = 1;
   g.C = h1;
   g.ldc = hid;
+  g.max_ctas = g_cap;
   if (up_low) {
     g.amode = A_UPCAT;
     g.A = up_low;
@@ -300,6 +307,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.post_shift = post_t;
   g2.C = out;
   g2.ldc = ldc;
+  g2.max_ctas = g_cap;
   CK(launch_gemm(g2, st));
   prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
   return 0;
@@ -324,6 +332,7 @@ int run_dense(const casync_plan* p, const char* wname, const char* bname, const 
   }
   g.C = C;
   g.ldc = ldc;
+  g.max_ctas = g_cap;
   CK(launch_gemm(g, st));
   prof_mark(wname, 2.0 * M * K * N, 2.0 * M * (K + N * (res_pre ? 2 : 1)));
   return 0;
@@ -347,6 +356,7 @@ int run_conv3x3(const casync_plan* p, const char* pre, const bf16* in, int Hin, 
   g.leaky = 1;
   g.C = out;
   g.ldc = Cout;
+  g.max_ctas = g_cap;
   CK(launch_gemm(g, st));
   prof_mark(pre, 2.0 * g.M * g.K * g.N, 2.0 * (batch * Hin * Hin * Cin + (double)g.M * Cout));
   return 0;
@@ -358,29 +368,33 @@ int run_audio(const casync_plan* p, const float* audio, bf16* out, int ldo, cons
   CK(launch_audio_prep(audio, w["aud_in"], batch, st));
   prof_mark("audio.prep", 0, 6.0 * batch * 32768);
   int e;
-  if ((e = run_ir(p, IR_AUD1, w["aud_in"], nullptr, w["a1"], 64, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
-  if ((e = run_ir(p, IR_AUD2, w["a1"], nullptr, w["a2"], 128, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD1, w["aud_in"], nullptr, w["a1"], 64, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD2, w["a1"], nullptr, w["a2"], 128, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
   if ((e = run_conv3x3(p, "audio_model.conv3", w["a2"], 32, 128, 1, 256, w["a3"], batch, st))) return e;
-  if ((e = run_ir(p, IR_AUD4, w["a3"], nullptr, w["a4"], 256, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+  if ((e = run_ir(p, IR_AUD4, w["a3"], nullptr, w["a4"], 256, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
   if ((e = run_conv3x3(p, "audio_model.conv5", w["a4"], 16, 256, 3, 512, w["a5"], batch, st))) return e;
-  if ((e = run_ir(p, IR_AUD6, w["a5"], nullptr, w["a6"], 512, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
-  return run_ir(p, IR_AUD7, w["a6"], nullptr, out, ldo, w["h1"], w["h2"], p->w<float>("audio_model.bn7|s"),
+  if ((e = run_ir(p, IR_AUD6, w["a5"], nullptr, w["a6"], 512, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
+  return run_ir(p, IR_AUD7, w["a6"], nullptr, out, ldo, w["ah1"], w["ah2"], p->w<float>("audio_model.bn7|s"),
                 p->w<float>("audio_model.bn7|t"), batch, st);
 }
 
 // module/unet.py:323-336: tx = bn_tx(cat + mlp(cat)); 4 x AttentionBlock; kx = leaky(bn_kx(tx + sum ox_i)).
 // `cat` = [x5 | audio] with leading dimension 1024.
+int run_kv(const casync_plan* p, const bf16* cat, const Workspace& w, int batch, cudaStream_t st) {
+  // keys/values of all four blocks depend only on the audio half of `cat`: one GEMM, N = 4*(64+512)
+  return run_dense(p, "attention_blocks|kv_w", "attention_blocks|kv_b", cat + 512, 1024, batch * 100, 512, 2304,
+                   w["kvall"], 2304, 0, nullptr, 0, nullptr, st);
+}
+
 int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const Workspace& w, int batch,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool kv_done = false) {
   const int M = batch * 100;
   int e;
   if ((e = run_dense(p, "mlp_fusion.fc1|w", "mlp_fusion.fc1|b", cat, 1024, M, 1024, 1024, w["fc1"], 1024, 1, nullptr, 0,
                      nullptr, st))) return e;
   if ((e = run_dense(p, "mlp_fusion.fc2|w", "mlp_fusion.fc2|b", w["fc1"], 1024, M, 1024, 1024, w["tx"], 1024, 0, cat,
                      1024, "mlp_fusion.fc2|rs", st))) return e;
-  // keys/values of all four blocks depend only on the audio half of `cat`: one GEMM, N = 4*(64+512)
-  if ((e = run_dense(p, "attention_blocks|kv_w", "attention_blocks|kv_b", cat + 512, 1024, M, 512, 2304, w["kvall"],
-                     2304, 0, nullptr, 0, nullptr, st))) return e;
+  if (!kv_done && (e = run_kv(p, cat, w, batch, st))) return e;
   const char* oxn[4] = {"ox0", "ox1", "ox2", "ox3"};
   const bf16* ox = w["tx"];
   for (int j = 0; j < 4; ++j) {
@@ -417,15 +431,41 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
   const char* dn_o[4] = {"x2", "x3", "x4", "cat"};
   const bf16* cur = w["x1"];
-  for (int l = 0; l < 4; ++l) {
+  // The audio encoder (and the key/value GEMM behind it) is independent of the face encoder.  Its kernels and the
+  // low-resolution half of the face encoder are both latency-bound at small batch, so they run side by side: the
+  // audio branch on the plan's side stream, each branch's persistent kernels capped to half of the SMs.
+  const bool overlap = p->overlap && p->side && !g_prof;
+  auto down_block = [&](int l) -> int {
     const int i0 = IR_DOWN + 2 * l;
-    if ((e = run_ir(p, i0, cur, nullptr, w[dn_t[l]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+    int e2;
+    if ((e2 = run_ir(p, i0, cur, nullptr, w[dn_t[l]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e2;
     const int ldo = l == 3 ? 1024 : kIr[i0 + 1].cout;  // x5 lands in the left half of `cat`
-    if ((e = run_ir(p, i0 + 1, w[dn_t[l]], nullptr, w[dn_o[l]], ldo, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+    if ((e2 = run_ir(p, i0 + 1, w[dn_t[l]], nullptr, w[dn_o[l]], ldo, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e2;
     cur = w[dn_o[l]];
+    return 0;
+  };
+  if ((e = down_block(0))) return e;
+  if (overlap) {
+    const int i0 = IR_DOWN + 2;   // down2.0 (fused, all SMs) still before the fork
+    if ((e = run_ir(p, i0, cur, nullptr, w[dn_t[1]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
+    CK(cudaEventRecord(p->ev_fork, st));
+    CK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    g_cap = p->num_sms / 2;
+    e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, p->side);
+    if (!e) e = run_kv(p, w["cat"], w, batch, p->side);
+    if (!e) e = run_ir(p, i0 + 1, w[dn_t[1]], nullptr, w[dn_o[1]], kIr[i0 + 1].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st);
+    cur = w[dn_o[1]];
+    for (int l = 2; l < 4 && !e; ++l) e = down_block(l);
+    g_cap = 0;
+    if (e) return e;
+    CK(cudaEventRecord(p->ev_join, p->side));
+    CK(cudaStreamWaitEvent(st, p->ev_join, 0));
+  } else {
+    for (int l = 1; l < 4; ++l)
+      if ((e = down_block(l))) return e;
+    if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st))) return e;
   }
-  if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st))) return e;
-  if ((e = run_fusion_attention(p, w["cat"], w["kx"], w, batch, st))) return e;
+  if ((e = run_fusion_attention(p, w["cat"], w["kx"], w, batch, st, overlap))) return e;
   const char* fz[5] = {"kx", "f0", "f1", "f2", "fuse"};
   for (int l = 0; l < 4; ++l)
     if ((e = run_ir(p, IR_FUSE + l, w[fz[l]], nullptr, w[fz[l + 1]], kIr[IR_FUSE + l].cout, w["h1"], w["h2"], nullptr,
@@ -496,6 +536,16 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
     if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
   }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
+  if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
+  if (const char* c = getenv("CASYNC_OVERLAP")) p->overlap = atoi(c) > 0;          // A/B switch for the two-stream overlap
+  if (p->overlap) {
+    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      delete p;
+      return fail(CASYNC_ECUDA, "cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   if (const char* c = getenv("CASYNC_CHUNK")) {
     int v = atoi(c);
     if (v > 0) p->chunk = v;
@@ -522,6 +572,14 @@ void casync_plan_destroy(casync_plan* plan) {
       fprintf(stderr, "  [%.3g cycles]\n", tot);
     }
     cudaFree(plan->phase_dbg);
+  }
+  if (plan) {
+    if (plan->side) {
+      cudaStreamSynchronize(plan->side);
+      cudaStreamDestroy(plan->side);
+    }
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
   }
   delete plan;
 }
