@@ -7,5 +7,6 @@ forward raises.
 """
 from .unet import Model  # noqa: F401
 from .sharding import frame_shard, shard_sizes  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["Model", "frame_shard", "shard_sizes"]
+__all__ = ["Model", "HostPipeline", "frame_shard", "shard_sizes"]

@@ -366,12 +366,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
                 v[q] = fmaxf(v[q], kLeaky * v[q]);
               }
             }
-            uint4 o;
-            o.x = pack_bf16(v[0], v[1]);
-            o.y = pack_bf16(v[2], v[3]);
-            o.z = pack_bf16(v[4], v[5]);
-            o.w = pack_bf16(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.C + (size_t)m * p.ldc + n + 8 * g) = o;
+            if (p.vt && n0 >= p.vt_col0) {   // transposed store of a value projection (see GemmArgs::vt)
+              const int frame = m / 100, key = m - frame * 100;
+              const int colv = n + 8 * g - p.vt_col0;   // j * 512 + channel
+              __nv_bfloat16* dst = p.vt + ((size_t)frame * 2048 + colv) * 128 + key;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) dst[q * 128] = __float2bfloat16_rn(v[q]);
+            } else {
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]);
+              o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]);
+              o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(p.C + (size_t)m * p.ldc + n + 8 * g) = o;
+            }
           }
         }
       }

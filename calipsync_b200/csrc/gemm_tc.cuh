@@ -28,6 +28,11 @@ struct GemmArgs {
   __nv_bfloat16* C;
   int ldc;
   int max_ctas;             // 0: one CTA per SM; >0: cap (two branches of the forward sharing the GPU on two streams)
+  // key/value GEMM of the attention blocks: columns >= vt_col0 (the four 512-channel value projections) are stored
+  // TRANSPOSED per frame, vt[frame][j][channel][key] with 128 keys per row (100 used), so that the attention kernel
+  // can use V^T as a K-major B operand of tcgen05.mma (module/unet.py:215: out = V . attn^T)
+  __nv_bfloat16* vt;
+  int vt_col0;
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);  // returns 0 or cudaError

@@ -9,75 +9,171 @@ namespace casync {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// inc: 32x8 output tile per CTA, 34x10 input halo.  The depthwise conv zero-pads the HIDDEN tensor
-// (module/unet.py:21-27), so hidden values of out-of-image halo pixels are exactly 0, not pw1(0).
+// inc (InConvDw, module/unet.py:58-67): 6 -> (12) -> 32 at 160x160, fp32 NCHW in -> bf16 NHWC out.
+// CTA = 16x16 output pixels = two 128-row UMMA tiles, 18x18 input halo.
+//   pw1 6->12 (+BN+leaky)   CUDA cores, fp32, once per halo pixel; the depthwise conv zero-pads the HIDDEN tensor
+//                           (module/unet.py:21-27), so hidden values of out-of-image halo pixels are exactly 0
+//   dw 3x3 (+BN+leaky)      CUDA cores, packed bf16x2 over the 6 channel pairs, from shared memory
+//   pw2 12->32 (+BN+leaky)  68 % of the block's MACs: ONE tcgen05.mma per tile (M128 N32 K16, K zero-padded
+//                           12->16), A = depthwise output written as a SWIZZLE_128B tile, D in TMEM (32 columns)
 // ------------------------------------------------------------------------------------------------
-constexpr int kIncTW = 32, kIncTH = 8, kIncHW = kIncTW + 2, kIncHH = kIncTH + 2, kIncHalo = kIncHW * kIncHH;
+constexpr int kIncT = 16, kIncH = kIncT + 2, kIncHalo = kIncH * kIncH;
+struct IncSmem {
+  uint8_t a2[2][16384];          // two [128 rows x 128 B] SWIZZLE_128B tiles; only K = 16 (32 B per row) is used
+  uint8_t w2[4096];              // packed pw2 weights: 32 rows x 128 B (packer: pack_gemm_weight)
+  uint4 hid[kIncHalo][2];        // 16 bf16 per halo pixel (12 hidden channels + 4 zeros)
+  uint32_t wd2[9][8];            // depthwise taps as bf16x2 channel pairs (pairs 6,7 = 0)
+  uint32_t bd2[8];
+  uint64_t bar_w, bar_mma;
+  uint32_t tmem_slot;
+};
+// the fp32 input halo (6 x 324 floats) lives in a2[1]: it is dead before the depthwise phase writes the A tiles
+static_assert(6 * kIncHalo * 4 <= 16384, "input halo must fit the aliased tile");
 
 __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                  const uint8_t* __restrict__ w2t,
                                                   const __grid_constant__ IncParams w) {
-  __shared__ float s_in[6][kIncHalo];
-  __shared__ float s_h[12][kIncHalo];
-  const int tid = threadIdx.x;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  IncSmem& s = *reinterpret_cast<IncSmem*>(smem_raw + (base - smem_u32(smem_raw)));
+  float(*s_in)[kIncHalo] = reinterpret_cast<float(*)[kIncHalo]>(s.a2[1]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
-  pdl_wait();
-  const int x0 = blockIdx.x * kIncTW, y0 = blockIdx.y * kIncTH, b = blockIdx.z;
-  const float* xb = x + (size_t)b * 6 * 25600;
-  for (int idx = tid; idx < 6 * kIncHalo; idx += 256) {
-    int c = idx / kIncHalo, r = idx - c * kIncHalo;
-    int yy = r / kIncHW, xx = r - yy * kIncHW;
-    int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
-    float v = 0.f;
-    if (gy >= 0 && gy < 160 && gx >= 0 && gx < 160) v = __ldg(xb + (size_t)c * 25600 + gy * 160 + gx);
-    s_in[c][r] = v;
+  const uint32_t bar_w = smem_u32(&s.bar_w), bar_mma = smem_u32(&s.bar_mma);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(bar_w, 4096);
+    bulk_g2s(smem_u32(s.w2), w2t, 4096, bar_w);
   }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&s.tmem_slot), 64);
+    tmem_relinquish();
+  }
+  if (tid >= 64 && tid < 64 + 80) {   // taps / bias of the depthwise conv -> bf16x2 pairs
+    const int i = tid - 64, t9 = i >> 3, q = i & 7;
+    const float lo = q < 6 ? (t9 < 9 ? w.wd[t9 * 12 + 2 * q] : w.bd[2 * q]) : 0.f;
+    const float hi = q < 6 ? (t9 < 9 ? w.wd[t9 * 12 + 2 * q + 1] : w.bd[2 * q + 1]) : 0.f;
+    if (t9 < 9) s.wd2[t9][q] = pack_bf16(lo, hi);
+    else s.bd2[q] = pack_bf16(lo, hi);
+  }
+  const int x0 = blockIdx.x * kIncT, y0 = blockIdx.y * kIncT, b = blockIdx.z;
+  pdl_wait();
+  // ---- input halo, fp32 NCHW -> smem
+  const float* xb = x + (size_t)b * 6 * 25600;
+  {
+    constexpr int NL = (6 * kIncHalo + 255) / 256;   // 8 loads per thread, all in flight before the first store
+    float v[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + 256 * i;
+      const int c = idx / kIncHalo, r = idx - c * kIncHalo;
+      const int yy = r / kIncH, xx = r - yy * kIncH;
+      const int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+      v[i] = (idx < 6 * kIncHalo && gy >= 0 && gy < 160 && gx >= 0 && gx < 160)
+                 ? __ldg(xb + (size_t)c * 25600 + gy * 160 + gx) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + 256 * i;
+      if (idx < 6 * kIncHalo) (&s_in[0][0])[idx] = v[i];
+    }
+  }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_slot;
+  // ---- pw1 (+BN+leaky) per halo pixel -> 12 hidden channels as bf16
   for (int r = tid; r < kIncHalo; r += 256) {
-    int yy = r / kIncHW, xx = r - yy * kIncHW;
-    int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
-    bool inside = gy >= 0 && gy < 160 && gx >= 0 && gx < 160;
+    const int yy = r / kIncH, xx = r - yy * kIncH;
+    const int gy = y0 - 1 + yy, gx = x0 - 1 + xx;
+    const bool inside = gy >= 0 && gy < 160 && gx >= 0 && gx < 160;
     float in[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) in[c] = s_in[c][r];
+    uint32_t h[6];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      float a = w.b1[j];
+    for (int q = 0; q < 6; ++q) {
+      float a0 = w.b1[2 * q], a1 = w.b1[2 * q + 1];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) a = fmaf(w.w1[j * 6 + c], in[c], a);
-      s_h[j][r] = inside ? leaky(a) : 0.f;
+      for (int c = 0; c < 6; ++c) {
+        a0 = fmaf(w.w1[(2 * q) * 6 + c], in[c], a0);
+        a1 = fmaf(w.w1[(2 * q + 1) * 6 + c], in[c], a1);
+      }
+      h[q] = inside ? pack_bf16(leaky(a0), leaky(a1)) : 0u;
     }
+    s.hid[r][0] = make_uint4(h[0], h[1], h[2], h[3]);
+    s.hid[r][1] = make_uint4(h[4], h[5], 0u, 0u);
   }
   __syncthreads();
-  const int ty = tid >> 5, tx = tid & 31;
-  float h2[12];
+  // ---- depthwise 3x3 (+BN+leaky): thread = one output pixel, 6 channel pairs -> row of the A tile
+  {
+    const int oy = tid >> 4, ox = tid & 15;
+    __nv_bfloat162 acc[6];
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    float a = w.bd[j];
+    for (int q = 0; q < 6; ++q) acc[q] = *reinterpret_cast<const __nv_bfloat162*>(&s.bd2[q]);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) a = fmaf(w.wd[(ky * 3 + kx) * 12 + j], s_h[j][(ty + ky) * kIncHW + tx + kx], a);
-    h2[j] = leaky(a);
-  }
-  __nv_bfloat16* o = out + ((size_t)b * 25600 + (size_t)(y0 + ty) * 160 + x0 + tx) * 32;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int r = (oy + ky) * kIncH + ox + kx;
+        const uint4 h0 = s.hid[r][0];
+        const uint2 h1 = *reinterpret_cast<const uint2*>(&s.hid[r][1]);
+        const uint32_t hv[6] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y};
+        const uint4 w0 = *reinterpret_cast<const uint4*>(&s.wd2[ky * 3 + kx][0]);   // uniform address: broadcast
+        const uint2 w1 = *reinterpret_cast<const uint2*>(&s.wd2[ky * 3 + kx][4]);
+        const uint32_t wv[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float v[8];
+        for (int q = 0; q < 6; ++q)
+          acc[q] = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&wv[q]),
+                           *reinterpret_cast<const __nv_bfloat162*>(&hv[q]), acc[q]);
+      }
+    const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
+    uint32_t o[6];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int n = g * 8 + e;
-      float a = w.b2[n];
-#pragma unroll
-      for (int j = 0; j < 12; ++j) a = fmaf(w.w2[n * 12 + j], h2[j], a);
-      v[e] = leaky(a);
+    for (int q = 0; q < 6; ++q) {
+      const __nv_bfloat162 v = __hmax2(acc[q], __hmul2(acc[q], kslope));
+      o[q] = *reinterpret_cast<const uint32_t*>(&v);
     }
-    uint4 q;
-    q.x = pack_bf16(v[0], v[1]);
-    q.y = pack_bf16(v[2], v[3]);
-    q.z = pack_bf16(v[4], v[5]);
-    q.w = pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(o)[g] = q;
+    uint8_t* tile = s.a2[tid >> 7];
+    const uint32_t row = tid & 127;
+    *reinterpret_cast<uint4*>(tile + sw128_off(row, 0)) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(tile + sw128_off(row, 1)) = make_uint4(o[4], o[5], 0u, 0u);
   }
+  fence_proxy_async();
+  __syncthreads();
+  // ---- pw2 on the tensor core: D[tile] = A2[tile] (128 x 16) . W2^T (16 x 32)
+  if (tid == 0) {
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+    const uint64_t bdesc = umma_desc_sw128(smem_u32(s.w2));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) umma_bf16(tmem + t * 32, umma_desc_sw128(smem_u32(s.a2[t])), bdesc, idesc, 0);
+    umma_commit(bar_mma);
+  }
+  // ---- epilogue: TMEM -> +bias, leaky -> bf16 NHWC (64 B per pixel)
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  {
+    const int tile = warp >> 2, lg = warp & 3;
+    const int p = tile * 128 + lg * 32 + lane, oy = p >> 4, ox = p & 15;
+    uint32_t acc[32];
+    tmem_ld32(tmem + tile * 32 + ((uint32_t)(lg * 32) << 16), acc);
+    tmem_ld_wait32(acc);
+    uint4* o = reinterpret_cast<uint4*>(out + ((size_t)b * 25600 + (size_t)(y0 + oy) * 160 + x0 + ox) * 32);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = leaky(__uint_as_float(acc[g * 8 + e]) + w.b2[g * 8 + e]);
+      o[g] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -179,116 +275,157 @@ __global__ void __launch_bounds__(256) audio_prep_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention core.  CTA = (channel quarter, frame), 10 warps; warp w owns query rows 10w..10w+9 as two
-// groups of 5.  S = q k^T and the row softmax stay in registers (lane owns keys lane+32t), P goes to
-// shared memory only for the warp's own rows, then O = P V over this CTA's 128 value channels.
-// Softmax has no 1/sqrt(d) scale (module/unet.py:212-213).
+// attention core on the tensor cores (module/unet.py:209-217; no 1/sqrt(d) scale, :212-213).
+// CTA = (half of the 512 value channels, frame); 100 query tokens (visual) x 100 key tokens (audio).
+//   S = Q K^T        tcgen05.mma M128 N112 K64: Q, K tiles (rows >= 100 zero-filled) in SWIZZLE_128B smem -> TMEM
+//   P = softmax(S)   4 warps, thread = query row: tcgen05.ld -> fp32 max / exp / sum -> bf16 P tile in smem
+//   O = P V          tcgen05.mma M128 N256 K112: B operand = V^T rows (channel-major, written transposed by the
+//                    key/value GEMM's epilogue), keys 100..111 zeroed in smem
+//   out = gamma O + x   8 warps drain TMEM, add the p_1 output, store bf16
 // ------------------------------------------------------------------------------------------------
 constexpr int kT = 100;  // tokens per frame (10x10)
 struct AttnSmem {
-  uint32_t q2[kT][32];     // q[i][2d..2d+1] packed bf16x2
-  uint32_t kT2[32][kT];    // k[j][2d..2d+1] packed, transposed
-  uint2 v4[kT][32];        // v[j][4*lane..4*lane+3] (this CTA's 128 channels)
-  float P[kT][kT];
+  uint8_t q[16384];        // [128 rows x 128 B]: 64 query channels
+  uint8_t k[16384];        // [128 rows x 128 B]: keys (N operand of S), rows 100.. zero
+  uint8_t p[2][16384];     // P as A operand: k-blocks of 64 keys
+  uint8_t vt[2][32768];    // V^T rows (256 channels of this CTA) x k-blocks of 64 keys
+  uint64_t bar_s, bar_o;
+  uint32_t tmem_slot;
 };
 
-__global__ void __launch_bounds__(320) attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
-                                                        const __nv_bfloat16* __restrict__ k,
-                                                        const __nv_bfloat16* __restrict__ v, int ldkv,
-                                                        const __nv_bfloat16* __restrict__ x, int ldx,
-                                                        __nv_bfloat16* __restrict__ out, float gamma) {
+__global__ void __launch_bounds__(256, 1) attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq,
+                                                           const __nv_bfloat16* __restrict__ k, int ldk,
+                                                           const __nv_bfloat16* __restrict__ vt,
+                                                           const __nv_bfloat16* __restrict__ x, int ldx,
+                                                           __nv_bfloat16* __restrict__ out, float gamma) {
   extern __shared__ uint8_t smem_raw[];
-  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw);
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw + (base - smem_u32(smem_raw)));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int quarter = blockIdx.x;
+  const int half = blockIdx.x;
   const size_t row0 = (size_t)blockIdx.y * kT;
-  for (int idx = tid; idx < kT * 32; idx += 320) {
-    const int j = idx >> 5, d2 = idx & 31;
-    s.q2[j][d2] = __ldg(reinterpret_cast<const uint32_t*>(q + (row0 + j) * ldq) + d2);
-    s.kT2[d2][j] = __ldg(reinterpret_cast<const uint32_t*>(k + (row0 + j) * ldkv) + d2);
-    s.v4[j][d2] = __ldg(reinterpret_cast<const uint2*>(v + (row0 + j) * ldkv + quarter * 128) + d2);
+  pdl_launch_dependents();
+  const uint32_t bar_s = smem_u32(&s.bar_s), bar_o = smem_u32(&s.bar_o);
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
   }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&s.tmem_slot), 512);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  // ---- operand tiles -> shared memory (16-byte cp.async chunks, 128B swizzle applied in the address)
+  const uint32_t sq = smem_u32(s.q), sk = smem_u32(s.k), sp = smem_u32(s.p[0]), sv = smem_u32(s.vt[0]);
+  for (int i = tid; i < 128 * 8; i += 256) {
+    const int r = i >> 3, c = i & 7;
+    const bool valid = r < kT;
+    cp_async16(sq + sw128_off(r, c), valid ? q + (row0 + r) * ldq + c * 8 : q, valid);
+    cp_async16(sk + sw128_off(r, c), valid ? k + (row0 + r) * ldk + c * 8 : k, valid);
+  }
+  const __nv_bfloat16* vb = vt + ((size_t)blockIdx.y * 2048 + half * 256) * 128;
+  for (int i = tid; i < 256 * 14; i += 256) {     // keys 0..111: 14 chunks of 8 keys per channel row
+    const int n = i / 14, c = i - n * 14;
+    cp_async16(sv + (c >> 3) * 32768 + sw128_off(n, c & 7), vb + (size_t)n * 128 + c * 8, c < 13);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();   // every thread's copies have landed before the fix-up below touches other threads' chunks
+  // keys 100..103 share a chunk with keys 96..99: clear them (the V^T buffer's padding is never written)
+  *reinterpret_cast<uint2*>(s.vt[1] + sw128_off(tid, 4) + 8) = make_uint2(0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
-#pragma unroll 1
-  for (int grp = 0; grp < 2; ++grp) {
-    const int i0 = warp * 10 + grp * 5;
-    float sc[5][4];
+  tc_fence_after();
+  const uint32_t tmem = s.tmem_slot;
+  if (tid == 0) {   // S[128 x 112] = Q K^T
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 112);
+    const uint64_t ad = umma_desc_sw128(sq), bd = umma_desc_sw128(sk);
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+    for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem, ad + 2 * ks, bd + 2 * ks, idesc, ks != 0);
+    umma_commit(bar_s);
+  }
+  if (warp < 4) {   // row softmax: thread = query row
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    float sc[112];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) sc[r][t] = 0.f;
-#pragma unroll 4
-    for (int d2 = 0; d2 < 32; ++d2) {
-      uint32_t kk[4];
+    for (int c0 = 0; c0 < 112; c0 += 16) tmem_ld16(trow + c0, reinterpret_cast<uint32_t*>(sc) + c0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) kk[t] = (lane + 32 * t < kT) ? s.kT2[d2][lane + 32 * t] : 0u;
+    for (int c0 = 0; c0 < 112; c0 += 16) tmem_ld_wait16(reinterpret_cast<uint32_t*>(sc) + c0);
+    float mx = -INFINITY;
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const uint32_t qq = s.q2[i0 + r][d2];
-        const float ql = bf16_lo(qq), qh = bf16_hi(qq);
+    for (int j = 0; j < kT; ++j) mx = fmaxf(mx, sc[j]);
+    float sum = 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) sc[r][t] = fmaf(qh, bf16_hi(kk[t]), fmaf(ql, bf16_lo(kk[t]), sc[r][t]));
-      }
+    for (int j = 0; j < kT; ++j) {
+      sc[j] = __expf(sc[j] - mx);
+      sum += sc[j];
     }
+    const float inv = 1.f / sum;
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      float mx = -INFINITY;
+    for (int c = 0; c < 14; ++c) {   // chunk of 8 keys -> 16 B of the P tile (keys >= 100: zero)
+      uint32_t o[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (lane + 32 * t < kT) mx = fmaxf(mx, sc[r][t]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        sc[r][t] = (lane + 32 * t < kT) ? __expf(sc[r][t] - mx) : 0.f;
-        sum += sc[r][t];
+      for (int e = 0; e < 4; ++e) {
+        const int j = c * 8 + 2 * e;
+        o[e] = j < kT ? pack_bf16(sc[j] * inv, sc[j + 1] * inv) : 0u;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (lane + 32 * t < kT) s.P[i0 + r][lane + 32 * t] = sc[r][t] * inv;
+      *reinterpret_cast<uint4*>(s.p[c >> 3] + sw128_off(row, c & 7)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    __syncwarp();
-    float acc[5][4];
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {   // O[128 x 256] = P V  (K = 112 keys: 4 + 3 steps of 16)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+    for (int ks = 0; ks < 7; ++ks) {
+      const uint64_t ad = umma_desc_sw128(sp + (ks >> 2) * 16384) + 2 * (ks & 3);
+      const uint64_t bd = umma_desc_sw128(sv + (ks >> 2) * 32768) + 2 * (ks & 3);
+      umma_bf16(tmem + 128, ad, bd, idesc, ks != 0);
+    }
+    umma_commit(bar_o);
+  }
+  {   // out = gamma O + x: warp -> (TMEM lane quarter, half of this CTA's 256 channels)
+    const int lg = warp & 3, ch = warp >> 2;
+    const int row = lg * 32 + lane;
+    const bool valid = row < kT;
+    const size_t m = row0 + (valid ? row : 0);
+    const int cbase = half * 256 + ch * 128;
+    const __nv_bfloat16* xr = x + m * ldx + cbase;
+    __nv_bfloat16* orow = out + m * 512 + cbase;
+    uint4 xv[16];   // residual row fetched while the MMAs run
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-#pragma unroll 2
-    for (int j = 0; j < kT; j += 4) {
-      float4 pr[5];
+    for (int i = 0; i < 16; ++i) xv[i] = valid ? *reinterpret_cast<const uint4*>(xr + 8 * i) : make_uint4(0, 0, 0, 0);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
 #pragma unroll
-      for (int r = 0; r < 5; ++r) pr[r] = *reinterpret_cast<const float4*>(&s.P[i0 + r][j]);
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + 128 + ch * 128 + c0 + ((uint32_t)(lg * 32) << 16), acc);
+      tmem_ld_wait32(acc);
+      if (valid) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const uint2 vv = s.v4[j + jj][lane];
-        const float v0 = bf16_lo(vv.x), v1 = bf16_hi(vv.x), v2 = bf16_lo(vv.y), v3 = bf16_hi(vv.y);
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t* pr = &xv[(c0 >> 3) + g].x;
+          uint32_t o[4];
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const float pp = jj == 0 ? pr[r].x : jj == 1 ? pr[r].y : jj == 2 ? pr[r].z : pr[r].w;
-          acc[r][0] = fmaf(pp, v0, acc[r][0]);
-          acc[r][1] = fmaf(pp, v1, acc[r][1]);
-          acc[r][2] = fmaf(pp, v2, acc[r][2]);
-          acc[r][3] = fmaf(pp, v3, acc[r][3]);
+          for (int e = 0; e < 4; ++e)
+            o[e] = pack_bf16(fmaf(gamma, __uint_as_float(acc[8 * g + 2 * e]), bf16_lo(pr[e])),
+                             fmaf(gamma, __uint_as_float(acc[8 * g + 2 * e + 1]), bf16_hi(pr[e])));
+          *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      const size_t off = (row0 + i0 + r) * 512 + quarter * 128 + lane * 4;
-      const uint2 xx = __ldg(reinterpret_cast<const uint2*>(x + (row0 + i0 + r) * ldx + quarter * 128 + lane * 4));
-      uint2 o;
-      o.x = pack_bf16(fmaf(gamma, acc[r][0], bf16_lo(xx.x)), fmaf(gamma, acc[r][1], bf16_hi(xx.x)));
-      o.y = pack_bf16(fmaf(gamma, acc[r][2], bf16_lo(xx.y)), fmaf(gamma, acc[r][3], bf16_hi(xx.y)));
-      *reinterpret_cast<uint2*>(out + off) = o;
-    }
-    __syncwarp();
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,15 +493,17 @@ __global__ void __launch_bounds__(256) outc_kernel(const __nv_bfloat16* __restri
 }  // namespace
 
 int kernels_init() {
-  int e = (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem));
+  int e = (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(AttnSmem) + 1024);
+  e |= (int)cudaFuncSetAttribute(inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IncSmem) + 1024);
   e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
   e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
   return e;
 }
 
-int launch_inc(const float* x, __nv_bfloat16* out, const IncParams& w, int batch, cudaStream_t st) {
-  dim3 grid(160 / kIncTW, 160 / kIncTH, batch);
-  return (int)launch_pdl(inc_kernel, grid, dim3(256), 0, st, x, out, w);
+int launch_inc(const float* x, __nv_bfloat16* out, const uint8_t* w2t, const IncParams& w, int batch, cudaStream_t st) {
+  dim3 grid(160 / kIncT, 160 / kIncT, batch);
+  return (int)launch_pdl(inc_kernel, grid, dim3(256), sizeof(IncSmem) + 1024, st, x, out, w2t, w);
 }
 
 int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
@@ -389,10 +528,10 @@ int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStr
   return (int)launch_pdl(audio_prep_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, audio, out, npix);
 }
 
-int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
+int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st) {
-  return (int)launch_pdl(attention_kernel, dim3(4, batch), dim3(320), sizeof(AttnSmem), st, q, ldq, k, v, ldkv, x, ldx,
-                         out, gamma);
+  return (int)launch_pdl(attention_kernel, dim3(2, batch), dim3(256), sizeof(AttnSmem) + 1024, st, q, ldq, k, ldk, vt, x,
+                         ldx, out, gamma);
 }
 
 int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,

@@ -4,8 +4,9 @@
 
 namespace casync {
 
-// `inc` (InConvDw, module/unet.py:58-67): one InvertedResidual 6 -> (12) -> 32 at 160x160, fully fused on
-// CUDA cores (K=6/12 is far below a UMMA tile).  Weights travel as kernel parameters (constant bank).
+// `inc` (InConvDw, module/unet.py:58-67): one InvertedResidual 6 -> (12) -> 32 at 160x160 in one kernel: pw1 and the
+// depthwise conv on CUDA cores (K = 6 is far below a UMMA tile), pw2 (12 -> 32, K padded to 16) on the tensor core.
+// The small weights travel as kernel parameters (constant bank); pw2 additionally as a packed bf16 UMMA tile.
 struct IncParams {
   float w1[12 * 6];   // [hidden][cin], BN folded
   float b1[12];
@@ -20,15 +21,18 @@ struct OutcParams {   // OutConv + outc_bn folded (module/unet.py:100-106, 342-3
   float pad_;
 };
 
-int launch_inc(const float* x_nchw, __nv_bfloat16* x1_nhwc, const IncParams& w, int batch, cudaStream_t st);
+int launch_inc(const float* x_nchw, __nv_bfloat16* x1_nhwc, const uint8_t* w2_tile, const IncParams& w, int batch,
+               cudaStream_t st);
 // depthwise 3x3, pad 1, stride 1|2, + folded BN bias + LeakyReLU.  NHWC bf16 -> NHWC bf16, wd fp32 [9][C].
 int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
                  int W, int C, int stride, cudaStream_t st);
 // audio window fp32 [B,32,32,32] NCHW -> bf16 NHWC
 int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st);
-// softmax(q k^T) v core of CrossAttention (module/unet.py:209-217) for one attention block:
+// softmax(q k^T) v core of CrossAttention (module/unet.py:209-217) for one attention block, on the tensor cores:
 //   out[m, c] = gamma * sum_j softmax_j(q[m,:].k[j,:]) v[j,c] + x[m,c]   (per frame: 100 queries x 100 keys)
-int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, const __nv_bfloat16* v, int ldkv,
+// q [M, 64] (pitch ldq), k [M, 64] (pitch ldk) row-major; vt = V^T per frame: [B][4 blocks][512][128 keys] with the
+// block offset already applied (frame stride 4*512*128); x, out: [M, 512] with pitches ldx, 512.
+int launch_attention(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* vt,
                      const __nv_bfloat16* x, int ldx, __nv_bfloat16* out, float gamma, int batch, cudaStream_t st);
 // kx = leaky(bn_kx(tx + ox0 + ox1 + ox2 + ox3))  (module/unet.py:329-336), fp32 sum of the bf16 stage tensors
 int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfloat16* o1, const __nv_bfloat16* o2,

@@ -105,6 +105,7 @@ const std::vector<Entry>& schema() {
   static std::vector<Entry> s;
   if (!s.empty()) return s;
   s.push_back({"inc.inconv.0|inc", sizeof(IncParams)});
+  s.push_back({"inc.inconv.0|w2t", packed_bytes(32, 12)});   // pw2 of `inc` as a UMMA tile (K padded 12 -> 64)
   for (int i = 1; i < kNumIr; ++i) {
     const IrDef& d = kIr[i];
     const int hid = 2 * d.cin;
@@ -165,7 +166,7 @@ const BufDef kBufs[] = {
     {"x1", 25600, 32},  {"x2", 6400, 64},    {"x3", 1600, 128},  {"x4", 400, 256},   {"cat", 100, 1024},
     {"d1t", 6400, 64},  {"d2t", 1600, 128},  {"d3t", 400, 256},  {"d4t", 100, 512},  {"aud_in", 1024, 32},
     {"a1", 1024, 64},   {"a2", 1024, 128},   {"a3", 256, 256},   {"a4", 256, 256},   {"a5", 100, 512},
-    {"a6", 100, 512},   {"fc1", 100, 1024},  {"tx", 100, 1024},  {"kvall", 100, 2304}, {"p1q", 100, 576},
+    {"a6", 100, 512},   {"fc1", 100, 1024},  {"tx", 100, 1024},  {"kall", 100, 256}, {"vt", 2048, 128}, {"p1q", 100, 576},
     {"att", 100, 512},   {"ox0", 100, 1024}, {"ox1", 100, 1024}, {"ox2", 100, 1024},
     {"ox3", 100, 1024}, {"kx", 100, 1024},   {"f0", 100, 512},   {"f1", 100, 512},   {"f2", 100, 256},
     {"fuse", 100, 256}, {"t_up1", 400, 128}, {"up1", 400, 128},  {"t_up2", 1600, 64}, {"up2", 1600, 64},
@@ -381,9 +382,25 @@ int run_audio(const casync_plan* p, const float* audio, bf16* out, int ldo, cons
 // module/unet.py:323-336: tx = bn_tx(cat + mlp(cat)); 4 x AttentionBlock; kx = leaky(bn_kx(tx + sum ox_i)).
 // `cat` = [x5 | audio] with leading dimension 1024.
 int run_kv(const casync_plan* p, const bf16* cat, const Workspace& w, int batch, cudaStream_t st) {
-  // keys/values of all four blocks depend only on the audio half of `cat`: one GEMM, N = 4*(64+512)
-  return run_dense(p, "attention_blocks|kv_w", "attention_blocks|kv_b", cat + 512, 1024, batch * 100, 512, 2304,
-                   w["kvall"], 2304, 0, nullptr, 0, nullptr, st);
+  // keys/values of all four blocks depend only on the audio half of `cat`: one GEMM, N = 4*64 + 4*512.  Keys land
+  // row-major in `kall` [M,256]; the value projections are stored transposed per frame in `vt` [B][4][512][128]
+  GemmArgs g{};
+  g.amode = A_PLAIN;
+  g.A = cat + 512;
+  g.lda = 1024;
+  g.M = batch * 100;
+  g.K = 512;
+  g.N = 2304;
+  g.W = p->w<uint8_t>("attention_blocks|kv_w");
+  g.bias = p->w<float>("attention_blocks|kv_b");
+  g.C = w["kall"];
+  g.ldc = 256;
+  g.vt = w["vt"];
+  g.vt_col0 = 256;
+  g.max_ctas = g_cap;
+  CK(launch_gemm(g, st));
+  prof_mark("attention_blocks|kv_w", 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
+  return 0;
 }
 
 int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const Workspace& w, int batch,
@@ -401,7 +418,7 @@ int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const 
     const std::string pre = "attention_blocks." + std::to_string(j) + "|";
     if ((e = run_dense(p, (pre + "p1q_w").c_str(), (pre + "p1q_b").c_str(), ox, 1024, M, 1024, 576, w["p1q"], 576, 0,
                        nullptr, 0, nullptr, st))) return e;
-    CK(launch_attention(w["p1q"] + 512, 576, w["kvall"] + j * 576, w["kvall"] + j * 576 + 64, 2304, w["p1q"], 576,
+    CK(launch_attention(w["p1q"] + 512, 576, w["kall"] + j * 64, 256, w["vt"] + (size_t)j * 512 * 128, w["p1q"], 576,
                         w["att"], p->gamma[j], batch, st));
     prof_mark(("attn" + std::to_string(j) + ".core").c_str(), 2.0 * batch * (100.0 * 100 * 64 + 100.0 * 100 * 512),
               2.0 * batch * 100 * (64 + 576 + 512 + 512));
@@ -426,7 +443,7 @@ int run_up(const casync_plan* p, int level, const bf16* low, const bf16* skip, b
 int forward_chunk(const casync_plan* p, const float* x, const float* audio, void* out, const Workspace& w, int batch,
                   unsigned flags, cudaStream_t st) {
   int e;
-  CK(launch_inc(x, w["x1"], p->inc, batch, st));
+  CK(launch_inc(x, w["x1"], p->w<uint8_t>("inc.inconv.0|w2t"), p->inc, batch, st));
   prof_mark("inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
   const char* dn_o[4] = {"x2", "x3", "x4", "cat"};

@@ -84,6 +84,8 @@ def build_entries(sd):
         elif part == "inc":
             w1, b1, wd, bd, w2, b2 = ir_parts(prefix)
             val = _f32(torch.cat([w1.reshape(-1), b1, wd.reshape(-1), bd, w2.reshape(-1), b2]))
+        elif part == "w2t":   # pw2 of `inc` for the tensor core: [32, 12] -> one k-block, K zero-padded to 64
+            val = pack_gemm_weight(ir_parts(prefix)[4])
         elif prefix in ("audio_model.conv3", "audio_model.conv5"):
             bn = prefix.replace("conv", "bn")
             s, t = _bn_fold(sd, bn)
@@ -110,11 +112,13 @@ def build_entries(sd):
             else:
                 val = _f32(st)
         elif prefix == "attention_blocks":
-            ws, bs = [], []
-            for j in range(4):
-                ca = "attention_blocks.%d.cross_attention." % j
-                ws += [sd[ca + "key_conv.weight"].double().flatten(1), sd[ca + "value_conv.weight"].double().flatten(1)]
-                bs += [sd[ca + "key_conv.bias"].double(), sd[ca + "value_conv.bias"].double()]
+            # rows ordered [k_0 .. k_3 (4 x 64) | v_0 | v_1 | v_2 | v_3 (4 x 512)]: the key block is stored row-major,
+            # the value blocks transposed per frame (GemmArgs::vt) for the tensor-core attention kernel
+            ca = "attention_blocks.%d.cross_attention."
+            ws = [sd[(ca % j) + "key_conv.weight"].double().flatten(1) for j in range(4)] + \
+                 [sd[(ca % j) + "value_conv.weight"].double().flatten(1) for j in range(4)]
+            bs = [sd[(ca % j) + "key_conv.bias"].double() for j in range(4)] + \
+                 [sd[(ca % j) + "value_conv.bias"].double() for j in range(4)]
             if part == "kv_w":
                 val = pack_gemm_weight(torch.cat(ws, 0))
             elif part == "kv_b":

@@ -83,8 +83,8 @@ class PackedNet:
             p = "attention_blocks.%d|" % j
             p1q = self.r(self.pw(ox, p + "p1q_w", p + "p1q_b", 576, 1024))
             p1, q = p1q[:, :512], p1q[:, 512:].reshape(B, 64, 100)
-            k = kv[:, j * 576: j * 576 + 64].reshape(B, 64, 100)
-            v = kv[:, j * 576 + 64: (j + 1) * 576].reshape(B, 512, 100)
+            k = kv[:, j * 64: (j + 1) * 64].reshape(B, 64, 100)
+            v = kv[:, 256 + j * 512: 256 + (j + 1) * 512].reshape(B, 512, 100)
             attn = torch.softmax(torch.bmm(q.permute(0, 2, 1), k), -1)
             o = torch.bmm(v, attn.permute(0, 2, 1)).reshape(B, 512, 10, 10)
             att = self.r(gamma[j] * o + p1)

@@ -140,3 +140,21 @@ def test_called_from_worker_thread_on_side_stream():
     t.start()
     t.join()
     assert torch.equal(got["out"], want)
+
+
+def test_host_pipeline_equals_direct_forward():
+    """HostPipeline (H2D / forward / D2H of consecutive batches on three streams) returns exactly what a direct
+    Model call returns, for more batches than slots, a ragged last batch, and the uint8 epilogue."""
+    from calipsync_b200 import HostPipeline
+    model, _ = make_model("R1")
+    batches = [O.make_inputs(n, 20 + i) for i, n in enumerate((4, 4, 4, 4, 3))]
+    want = [model(x.cuda(), a.cuda()).cpu() for x, a in batches]
+    want_u8 = [model.forward_uint8(x.cuda(), a.cuda()).cpu() for x, a in batches]
+    for uint8, ref in ((False, want), (True, want_u8)):
+        pipe = HostPipeline(model, 4, uint8=uint8)
+        outs = [torch.empty_like(r).pin_memory() for r in ref]
+        for (x, a), o in zip(batches, outs):
+            pipe.submit(x.pin_memory(), a.pin_memory(), o)
+        pipe.flush()
+        for o, r in zip(outs, ref):
+            assert torch.equal(o, r)

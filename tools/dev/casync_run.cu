@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> blob(total, 0);
   for (int i = 0; i < n; ++i) {
     const std::string part = names[i].substr(names[i].find('|') + 1);
-    const bool is_bf16 = part == "w1" || part == "w2" || part == "w" || part == "kv_w" || part == "p1q_w" || part == "b1_w";
+    const bool is_bf16 = part == "w1" || part == "w2" || part == "w" || part == "kv_w" || part == "p1q_w" || part == "b1_w" || part == "w2t";
     if (is_bf16) {
       uint16_t* p = reinterpret_cast<uint16_t*>(blob.data() + off[i]);
       for (size_t j = 0; j < sizes[i] / 2; ++j) p[j] = f2bf(0.03f * frand());
