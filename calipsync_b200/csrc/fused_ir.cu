@@ -38,7 +38,7 @@ namespace casync {
 namespace {
 
 constexpr int kGroup = 256;                 // threads per compute group (8 warps)
-constexpr int kProd = 128;                  // A1 producer threads (4 warps)
+constexpr int kProd = 96;                   // A1 producer threads (3 warps): 20 warps per CTA -> 96 registers per thread
 constexpr int kIssuerWarp = (2 * kGroup + kProd) / 32;
 constexpr int kThreads = 2 * kGroup + kProd + 32;   // group B + group A + producers + issuer warp
 constexpr int kTile = 128 * 128;            // bytes of one 128-row x 128 B swizzled tile
@@ -493,10 +493,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
           // (hy,hx) is row hy*16+hx of the swizzled tile: its XOR term depends on hx only, so three column bases
           // are computed once per item and rows are reached with immediate offsets (2048 B per window row).
           // Two adjacent output columns per item: 4 window columns feed 2 x 9 taps (4 independent FMA chains).
-          constexpr int RB = TOH > 7 ? 7 : TOH;       // rows per item (7 or 6)
-          constexpr int NITEM = 7 * (TOH / RB);       // 14 or 7 (<= 16 slots: one pass)
+          constexpr int RB = TOH > 7 ? 7 : 3;         // rows per item: 14 = 2 x 7 (TILES = 2), 6 = 2 x 3 (TILES = 1)
+          static_assert(TOH == 2 * RB, "two row blocks per column pair");
+          constexpr int NITEM = 14;                   // 7 column pairs x 2 row blocks (<= 16 slots: one pass)
           for (int item = slot; item < NITEM; item += 16) {
-            const int ox = TOH > 7 ? (item >> 1) * 2 : item * 2, oy0 = TOH > 7 ? (item & 1) * 7 : 0;
+            const int ox = (item >> 1) * 2, oy0 = (item & 1) * RB;
             uint32_t cb[4];
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) cb[kx] = hid + oy0 * 2048 + (ox + kx) * 128 + ((chunk ^ ((ox + kx) & 7)) << 4);
