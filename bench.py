@@ -256,6 +256,17 @@ def main():
     fps_e2e = world * B * args.steps / (ms_e2e / 1e3)
     ms_u8 = timed_pipeline(HostPipeline(net, B, uint8=True), host_out_u8, args.steps, max(3, args.warmup))
     fps_e2e_u8 = world * B * args.steps / (ms_u8 / 1e3)
+    # (d) SURVEY 8(f) rows 1+2: the caller's numpy work on the device too -- uint8 crops + frame indices in (HuBERT
+    # features of the clip uploaded once), uint8 frames out
+    gcpu = torch.Generator().manual_seed(5)
+    keep = host_sets
+    host_sets = [(torch.randint(0, 256, (B, 160, 160, 3), dtype=torch.uint8, generator=gcpu).pin_memory(),
+                  (torch.arange(B, dtype=torch.int32) + 64 * i).pin_memory()) for i in range(2)]
+    fpipe = HostPipeline(net, B, frames=True)
+    fpipe.set_features(torch.randn(1500, 2, 1024, generator=gcpu).pin_memory())
+    ms_fr = timed_pipeline(fpipe, host_out_u8, args.steps, max(3, args.warmup))
+    fps_e2e_fr = world * B * args.steps / (ms_fr / 1e3)
+    host_sets = keep
 
     if rank != 0:
         if world > 1:
@@ -330,7 +341,10 @@ def main():
                 "api": "HostPipeline(Model).submit: fp32 NCHW pinned host in -> Model forward -> fp32 NCHW pinned host out; "
                        "H2D / forward / D2H of consecutive steps overlap on three streams",
                 "sequential_value": fps_e2e_seq, "sequential_ms_per_step": ms_seq / args.steps,
-                "uint8_out_value": fps_e2e_u8, "uint8_out_d2h_bytes_per_step": B * 160 * 160 * 3},
+                "uint8_out_value": fps_e2e_u8, "uint8_out_d2h_bytes_per_step": B * 160 * 160 * 3,
+                "frames_api_value": fps_e2e_fr, "frames_api_h2d_bytes_per_step": B * (160 * 160 * 3 + 4),
+                "frames_api": "HostPipeline(frames=True): uint8 crops + frame indices in, uint8 frames out; input "
+                              "assembly (infer_api.py:99-145, 238-245) runs on the device"},
         "gpu_launches": net.launches_per_forward(B) * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "stages": stages[:12], "batch_sweep_frames_per_s": sweep,
     }

@@ -21,6 +21,7 @@ SYMBOLS = [
     ("casync_chunk_frames", _I, [_P]),
     ("casync_workspace_bytes", _SZ, [_P, _I]),
     ("casync_forward", _I, [_P, _P, _P, _P, _P, _I, C.c_uint, _P]),
+    ("casync_prepare_inputs", _I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     ("casync_stage_view", _I, [_P, _I, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     ("casync_launches_per_forward", _I64, [_P, _I]),
     ("casync_ir_count", _I, []),

@@ -255,6 +255,55 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input prologue: what FrameSynthesizer.process_batch does on the CPU per frame.
+//   crop_to_x:     uint8 HWC crop [B,160,160,3] -> fp32 NCHW [B,6,160,160] = cat([crop/255, masked crop/255]);
+//                  the mask is cv2.rectangle(img, (5, 5, 150, 145), 0, -1): rows 5..149 x cols 5..154
+//                  (image_infer_v1/tools/frame_synthesizer/infer_api.py:238-245).  float(u8) / 255.0f is the
+//                  IEEE division numpy performs, so the result is bit-identical to the caller's tensor.
+//   window_audio:  HuBERT features [T,2,1024] + frame indices -> [B,32,32,32]: rows idx-8 .. idx+7, zero rows
+//                  outside the clip, all-zero when the reference's truncated padding comes up short
+//                  (infer_api.py:99-145).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) crop_to_x_kernel(const uint8_t* __restrict__ crops, float* __restrict__ x,
+                                                        long npix) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const long b = p / 25600;
+  const int r = (int)(p - b * 25600), y = r / 160, xx = r - y * 160;
+  const uint8_t* src = crops + p * 3;
+  const float v0 = (float)src[0] / 255.0f, v1 = (float)src[1] / 255.0f, v2 = (float)src[2] / 255.0f;
+  const bool masked = y >= 5 && y <= 149 && xx >= 5 && xx <= 154;
+  float* o = x + b * 6 * 25600 + r;
+  o[0] = v0;
+  o[25600] = v1;
+  o[2 * 25600] = v2;
+  o[3 * 25600] = masked ? 0.f : v0;
+  o[4 * 25600] = masked ? 0.f : v1;
+  o[5 * 25600] = masked ? 0.f : v2;
+}
+
+__global__ void __launch_bounds__(256) window_audio_kernel(const float4* __restrict__ feats, int T,
+                                                           const int* __restrict__ frame_idx,
+                                                           float4* __restrict__ out, long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const long b = i >> 13;              // 32768 floats = 8192 float4 per frame
+  const int w = (int)(i & 8191), row = w >> 9, j = w & 511;   // 16 rows of 2*1024 floats = 512 float4
+  // the reference pads with zeros_like(auds[:pad]) -- never more rows than already collected -- and falls back to an
+  // all-zero feature when the window then has fewer than 16 rows (infer_api.py:126-145)
+  const int lo = frame_idx[b] - 8, hi = lo + 16;
+  const int pad_l = lo < 0 ? -lo : 0, pad_r = hi > T ? hi - T : 0;
+  const int n_valid = (hi < T ? hi : T) - (lo > 0 ? lo : 0);
+  const bool whole = n_valid > 0 && pad_l <= n_valid && pad_r <= n_valid + pad_l;
+  const int src = lo + row;
+  out[i] = (whole && src >= 0 && src < T) ? __ldg(feats + (size_t)src * 512 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // audio window: fp32 [B,32(c),32,32] -> bf16 [B,32,32,32(c)]; one thread = one pixel (reads are coalesced
 // across the warp for every channel, the 64 B result is written with four 16 B stores).
 // ------------------------------------------------------------------------------------------------
@@ -521,6 +570,15 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, c
   const dim3 grid((unsigned)(C / 64), (unsigned)bands, (unsigned)batch);
   if (stride == 2) return (int)launch_pdl(dw3x3_kernel<2>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
   return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
+}
+
+int launch_prepare_inputs(const uint8_t* crops, const float* feats, int T, const int* frame_idx, float* x, float* audio,
+                          int batch, cudaStream_t st) {
+  const long npix = (long)batch * 25600, n4 = (long)batch * 8192;
+  int e = (int)launch_pdl(crop_to_x_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, crops, x, npix);
+  if (e) return e;
+  return (int)launch_pdl(window_audio_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st,
+                         reinterpret_cast<const float4*>(feats), T, frame_idx, reinterpret_cast<float4*>(audio), n4);
 }
 
 int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st) {

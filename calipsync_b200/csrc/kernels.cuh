@@ -26,6 +26,10 @@ int launch_inc(const float* x_nchw, __nv_bfloat16* x1_nhwc, const uint8_t* w2_ti
 // depthwise 3x3, pad 1, stride 1|2, + folded BN bias + LeakyReLU.  NHWC bf16 -> NHWC bf16, wd fp32 [9][C].
 int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
                  int W, int C, int stride, cudaStream_t st);
+// caller-side input assembly on the device: uint8 HWC crops -> x [B,6,160,160] (reference face + masked face, /255)
+// and HuBERT features [T,2,1024] + frame indices -> audio windows [B,32,32,32] (infer_api.py:99-145, 238-245)
+int launch_prepare_inputs(const uint8_t* crops, const float* feats, int T, const int* frame_idx, float* x, float* audio,
+                          int batch, cudaStream_t st);
 // audio window fp32 [B,32,32,32] NCHW -> bf16 NHWC
 int launch_audio_prep(const float* audio, __nv_bfloat16* out, int batch, cudaStream_t st);
 // softmax(q k^T) v core of CrossAttention (module/unet.py:209-217) for one attention block, on the tensor cores:

@@ -668,6 +668,16 @@ int casync_forward_profiled(const casync_plan* plan, const float* x, const float
   return 0;
 }
 
+int casync_prepare_inputs(const uint8_t* crops_hwc, const float* feats, int n_feat_frames, const int32_t* frame_idx,
+                          float* x_nchw, float* audio, int batch, void* stream) {
+  if (!crops_hwc || !feats || !frame_idx || !x_nchw || !audio) return fail(CASYNC_EINVAL, "null argument");
+  if (batch <= 0 || n_feat_frames <= 0) return fail(CASYNC_EINVAL, "batch and feature length must be positive");
+  if (((uintptr_t)feats | (uintptr_t)audio) & 15) return fail(CASYNC_EINVAL, "feature / audio buffers must be 16-byte aligned");
+  CK(launch_prepare_inputs(crops_hwc, feats, n_feat_frames, frame_idx, x_nchw, audio, batch,
+                           reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int casync_stage_view(const casync_plan* plan, int batch, const char* name, size_t* offset, int64_t* rows,
                       int64_t* cols, int64_t* ld) {
   if (!plan || !name || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "stage views need batch <= chunk");

@@ -200,6 +200,44 @@ class Model(nn.Module):
         out = torch.empty(x.shape[0], 160, 160, 3, dtype=torch.uint8, device=x.device)
         return self._run(x, audio_feat, out, _lib.F_OUT_U8_HWC)
 
+    # ---- caller-side input assembly on the device ---------------------------------------------
+    @torch.no_grad()
+    def prepare_inputs(self, crops_u8, hubert_feats, frame_idx):
+        """What FrameSynthesizer.process_batch builds with numpy per frame (infer_api.py:99-145, 238-245), on the GPU:
+        crops_u8 uint8 [B,160,160,3] (= ``crop_img[4:164, 4:164]``), hubert_feats fp32 [T,2,1024] (device resident),
+        frame_idx int [B]  ->  (x fp32 [B,6,160,160], audio_feat fp32 [B,32,32,32]), bit-identical to the caller's."""
+        if not (crops_u8.is_cuda and hubert_feats.is_cuda and frame_idx.is_cuda):
+            raise RuntimeError("prepare_inputs needs CUDA tensors (there is no CPU path)")
+        if crops_u8.dtype != torch.uint8 or crops_u8.dim() != 4 or tuple(crops_u8.shape[1:]) != (160, 160, 3):
+            raise RuntimeError("crops must be uint8 [B,160,160,3], got %s %s" % (crops_u8.dtype, tuple(crops_u8.shape)))
+        if hubert_feats.dtype != torch.float32 or hubert_feats.dim() != 3 or tuple(hubert_feats.shape[1:]) != (2, 1024):
+            raise RuntimeError("hubert features must be float32 [T,2,1024], got %s %s"
+                               % (hubert_feats.dtype, tuple(hubert_feats.shape)))
+        b = crops_u8.shape[0]
+        if frame_idx.numel() != b or b == 0:
+            raise RuntimeError("need one frame index per crop")
+        dev = crops_u8.device
+        crops_u8, hubert_feats = crops_u8.contiguous(), hubert_feats.contiguous()
+        idx = frame_idx.to(torch.int32).contiguous()
+        x = torch.empty(b, 6, 160, 160, dtype=torch.float32, device=dev)
+        a = torch.empty(b, 32, 32, 32, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.load().casync_prepare_inputs(crops_u8.data_ptr(), hubert_feats.data_ptr(), hubert_feats.shape[0],
+                                                   idx.data_ptr(), x.data_ptr(), a.data_ptr(), b, ctypes.c_void_p(stream))
+        _lib.check(rc, "casync_prepare_inputs")
+        return x, a
+
+    @torch.no_grad()
+    def forward_frames(self, crops_u8, hubert_feats, frame_idx, out=None):
+        """crops + HuBERT features + frame indices -> uint8 [B,160,160,3] = floor(pred*255) in the caller's HWC layout:
+        prepare_inputs -> forward -> uint8 epilogue without leaving the device."""
+        x, a = self.prepare_inputs(crops_u8, hubert_feats, frame_idx)
+        self._check_inputs(x, a)
+        if out is None:
+            out = torch.empty(x.shape[0], 160, 160, 3, dtype=torch.uint8, device=x.device)
+        return self._run(x, a, out, _lib.F_OUT_U8_HWC)
+
     # ---- introspection for tests / profiling --------------------------------------------------------------------
     def stage(self, name, batch):
         """bf16 [rows, cols] view of a stage activation left in the workspace by the last forward (batch <= chunk)."""

@@ -71,6 +71,16 @@ CASYNC_API size_t casync_workspace_bytes(const casync_plan *plan, int batch);
 CASYNC_API int casync_forward(const casync_plan *plan, const float *x_nchw, const float *audio, void *out, void *workspace,
                    int batch, unsigned flags, void *stream);
 
+/* Replaces the caller-side input assembly of FrameSynthesizer.process_batch, on the device:
+ *   crops_hwc  uint8 [batch,160,160,3]: `crop_img[4:164, 4:164]` of infer_api.py:238 (channel order as the caller's)
+ *   feats      fp32 [n_feat_frames,2,1024]: the clip's HuBERT features, resident on the device
+ *   frame_idx  int32 [batch] (device): audio frame index of every output frame
+ * ->  x_nchw   fp32 [batch,6,160,160] = cat([crop/255, masked crop/255]) with the mask rectangle rows 5..149 x cols
+ *              5..154 zeroed (infer_api.py:239-245);  audio fp32 [batch,32,32,32] = feats[idx-8 : idx+8] reshaped,
+ *              zero rows outside the clip (infer_api.py:99-145).  Bit-identical to what the caller builds with numpy. */
+CASYNC_API int casync_prepare_inputs(const uint8_t *crops_hwc, const float *feats, int n_feat_frames,
+                                     const int32_t *frame_idx, float *x_nchw, float *audio, int batch, void *stream);
+
 /* Same as casync_forward, but records one CUDA event after every kernel launch, SYNCHRONISES the stream and
  * returns per-launch device time with the launch's algorithmic FLOPs and activation bytes (weights excluded).
  * Profiling aid for bench.py's roofline line; not for the timed throughput run. */

@@ -153,13 +153,20 @@ def make_inputs(batch, seed=0, frame_offset=0):
 def window_audio(features, indices):
     """HuBERT windowing, image_infer_v1/tools/frame_synthesizer/infer_api.py:99-145 (and
     dataset/dataset.py:39-56): rows idx-8..idx+8 of [T,2,1024], zero-padded at clip ends,
-    reshaped to [32,32,32]."""
+    reshaped to [32,32,32].
+
+    Exact, including the reference's quirk (:126-129): the padding is built as ``zeros_like(auds[:pad])``, i.e. it can
+    never be longer than the rows already collected; when that truncates it the window has fewer than 16 rows and the
+    reference falls back to an ALL-ZERO feature (:133-145).  For frame indices inside a clip of >= 16 feature frames
+    this never triggers; it does for indices past the clip end."""
     T = features.shape[0]
     out = torch.zeros(len(indices), 16, 2, 1024, dtype=features.dtype)
     for n, idx in enumerate(indices):
         lo, hi = idx - 8, idx + 8
+        pad_l, pad_r = max(0, -lo), max(0, hi - T)
         s_lo, s_hi = max(lo, 0), min(hi, T)
-        if s_hi > s_lo:
+        n_valid = s_hi - s_lo
+        if n_valid > 0 and pad_l <= n_valid and pad_r <= n_valid + pad_l:
             out[n, s_lo - lo:s_hi - lo] = features[s_lo:s_hi]
     return out.reshape(len(indices), 32, 32, 32)
 
@@ -167,6 +174,23 @@ def window_audio(features, indices):
 # --------------------------------------------------------------------------------------
 # the forward pass
 # --------------------------------------------------------------------------------------
+def assemble_x(crops_u8):
+    """Caller-side image assembly, image_infer_v1/tools/frame_synthesizer/infer_api.py:238-245 (twin:
+    dataset/dataset.py:129-132): crops_u8 uint8 [B,160,160,3] (= crop_img[4:164, 4:164]) -> fp32 [B,6,160,160] =
+    cat([crop, masked crop]) / 255 with cv2.rectangle(img, (5, 5, 150, 145), (0,0,0), -1) = rows 5..149 x cols 5..154
+    zeroed.  numpy float32 arithmetic, exactly as the reference."""
+    import numpy as np
+    crops = np.asarray(crops_u8)
+    out = []
+    for img in crops:
+        masked = img.copy()
+        masked[5:150, 5:155] = 0
+        real = img.transpose(2, 0, 1).astype(np.float32) / 255.0
+        masked = masked.transpose(2, 0, 1).astype(np.float32) / 255.0
+        out.append(np.concatenate([real, masked]))
+    return torch.from_numpy(np.stack(out))
+
+
 def _bn(sd, p, x):
     """eval-mode BatchNorm (running statistics), eps=1e-5."""
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],

@@ -158,3 +158,38 @@ def test_host_pipeline_equals_direct_forward():
         pipe.flush()
         for o, r in zip(outs, ref):
             assert torch.equal(o, r)
+
+
+def test_device_input_prologue_is_bit_exact_and_feeds_the_forward():
+    """casync_prepare_inputs (uint8 crops -> 6-channel tensor, HuBERT window gather) against the oracle's restatement
+    of the caller's numpy code -- integer/byte work and exact float32 divisions: bit-exact, incl. clip-end zero rows."""
+    model, _ = make_model("R1")
+    rs = np.random.RandomState(5)
+    crops = torch.from_numpy(rs.randint(0, 256, size=(5, 160, 160, 3), dtype=np.uint8))
+    feats = torch.from_numpy(rs.randn(37, 2, 1024).astype(np.float32))
+    idxs = [0, 3, 18, 36, 38]                         # clip start, interior, clip end, past the end (reference: zeros)
+    x, a = model.prepare_inputs(crops.cuda(), feats.cuda(), torch.tensor(idxs).cuda())
+    assert torch.equal(x.cpu(), O.assemble_x(crops.numpy()))
+    assert torch.equal(a.cpu(), O.window_audio(feats, idxs))
+    u = model.forward_frames(crops.cuda(), feats.cuda(), torch.tensor(idxs).cuda())
+    assert torch.equal(u, model.forward_uint8(x, a))
+
+
+def test_host_pipeline_frames_mode():
+    """frames mode of HostPipeline == prepare_inputs + forward_uint8 called directly."""
+    from calipsync_b200 import HostPipeline
+    model, _ = make_model("R1")
+    rs = np.random.RandomState(8)
+    feats = torch.from_numpy(rs.randn(60, 2, 1024).astype(np.float32))
+    pipe = HostPipeline(model, 4, frames=True)
+    pipe.set_features(feats.pin_memory())
+    batches = [(torch.from_numpy(rs.randint(0, 256, size=(n, 160, 160, 3), dtype=np.uint8)),
+                torch.arange(n, dtype=torch.int32) + 4 * i) for i, n in enumerate((4, 4, 4, 2))]
+    outs = [torch.empty(c.shape[0], 160, 160, 3, dtype=torch.uint8).pin_memory() for c, _ in batches]
+    for (c, idx), o in zip(batches, outs):
+        pipe.submit(c.pin_memory(), idx.pin_memory(), o)
+    pipe.flush()
+    fg = feats.cuda()
+    for (c, idx), o in zip(batches, outs):
+        x, a = model.prepare_inputs(c.cuda(), fg, idx.cuda())
+        assert torch.equal(o, model.forward_uint8(x, a).cpu())

@@ -41,3 +41,36 @@ def test_window_audio_equals_reference_arithmetic():
         if idx + 8 > 30:
             auds = torch.cat([auds, torch.zeros_like(auds[: idx + 8 - 30])], 0)
         assert torch.equal(got[n], auds.reshape(32, 32, 32))
+
+
+def test_input_assembly_equals_reference_code():
+    """oracle.assemble_x / window_audio against the reference's own code: FrameSynthesizer._get_audio_features called
+    unbound, and the image lines of process_batch (infer_api.py:238-245) executed verbatim with cv2."""
+    import os
+    import sys
+
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from conftest import REFERENCE_DIR, have_reference
+    if not have_reference():
+        pytest.skip("reference checkout not present on this machine")
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    from image_infer_v1.tools.frame_synthesizer.infer_api import FrameSynthesizer
+
+    rs = np.random.RandomState(3)
+    feats = rs.randn(40, 2, 1024).astype(np.float32)
+    idxs = [0, 1, 7, 8, 20, 32, 33, 39, 45, 60]
+    ref = FrameSynthesizer._get_audio_features(None, feats, idxs)
+    assert torch.equal(O.window_audio(torch.from_numpy(feats), idxs), torch.from_numpy(ref))
+
+    crops168 = rs.randint(0, 256, size=(3, 168, 168, 3), dtype=np.uint8)
+    want = []
+    for crop_img in crops168:                      # infer_api.py:238-245
+        img_real_ex = crop_img[4:164, 4:164].copy()
+        img_masked = cv2.rectangle(img_real_ex.copy(), (5, 5, 150, 145), (0, 0, 0), -1)
+        img_real_ex = img_real_ex.transpose(2, 0, 1).astype(np.float32) / 255.0
+        img_masked = img_masked.transpose(2, 0, 1).astype(np.float32) / 255.0
+        want.append(np.concatenate([img_real_ex, img_masked]))
+    got = O.assemble_x(crops168[:, 4:164, 4:164])
+    assert torch.equal(got, torch.from_numpy(np.stack(want)))
