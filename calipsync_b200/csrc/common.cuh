@@ -94,6 +94,19 @@ __device__ __forceinline__ void cp_async_wait() {
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a CONVERGED warp.  The single-thread roles (tcgen05.mma issue, TMA issue) run warp-uniformly and
+// predicate the instruction with this: under a divergent `if (lane == 0)` ptxas wraps every UTCHMMA in a
+// vote/ELECT loop with R2UR moves (measured ~135 cycles per tcgen05.mma issued).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)

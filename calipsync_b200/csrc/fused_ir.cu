@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
 
   if (warp == kIssuerWarp) {
     // =========================================== MMA issuer ====================================================
-    if (lane == 0 && n_mine > 0) {
+    // the whole (converged) warp walks the schedule and waits; one elected lane issues the tcgen05 instructions
+    if (n_mine > 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64), idesc2 = umma_idesc_bf16(128, COUT);
       auto gemm2 = [&](int v) {   // D2[patch] (+)= A2[v] . W2[:, chunk]^T
         const int pv = v / NC, cv = v - pv * NC, b = v & 1, k = v >> 1;
@@ -183,15 +184,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
         if (cv == 0) mbar_wait(bar(B_D2FREE), (pv & 1) ^ 1);
         T(3);
         tc_fence_after();
-        const uint64_t bd = umma_desc_sw128(sW2 + cv * COUT * 128);
+        if (elect_one()) {
+          const uint64_t bd = umma_desc_sw128(sW2 + cv * COUT * 128);
 #pragma unroll
-        for (int t = 0; t < A2T; ++t) {
-          const uint64_t ad = umma_desc_sw128(sA2 + b * C::kA2Buf + t * kTile);
+          for (int t = 0; t < A2T; ++t) {
+            const uint64_t ad = umma_desc_sw128(sA2 + b * C::kA2Buf + t * kTile);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tD2 + t * COUT, ad + 2 * ks, bd + 2 * ks, idesc2, (cv | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(tD2 + t * COUT, ad + 2 * ks, bd + 2 * ks, idesc2, (cv | ks) != 0);
+          }
+          umma_commit(bar(B_A2FREE + b));
+          if (cv == NC - 1) umma_commit(bar(B_D2FULL));
         }
-        umma_commit(bar(B_A2FREE + b));
-        if (cv == NC - 1) umma_commit(bar(B_D2FULL));
+        __syncwarp();
         T(4);
       };
       int u = 0;
@@ -204,20 +208,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
           mbar_wait(bar(B_D1FREE + b), (k & 1) ^ 1);
           T(1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int t = 0; t < TILES; ++t) {
+            for (int t = 0; t < TILES; ++t) {
 #pragma unroll
-            for (int kb = 0; kb < KB1; ++kb) {
-              const uint64_t ad = umma_desc_sw128(sA1 + ab * C::kA1Buf + (kb * TILES + t) * kTile);
-              const uint64_t bd = umma_desc_sw128(sW1 + (kb * CH + c * 64) * 128);
-              constexpr int KS_ALL = (CIN + 15) / 16;
-              const int ks_n = (KS_ALL - kb * 4) < 4 ? (KS_ALL - kb * 4) : 4;
-              for (int ks = 0; ks < ks_n; ++ks)
-                umma_bf16(tmem + (b * TILES + t) * 64, ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) != 0);
+              for (int kb = 0; kb < KB1; ++kb) {
+                const uint64_t ad = umma_desc_sw128(sA1 + ab * C::kA1Buf + (kb * TILES + t) * kTile);
+                const uint64_t bd = umma_desc_sw128(sW1 + (kb * CH + c * 64) * 128);
+                constexpr int KS_ALL = (CIN + 15) / 16;
+                const int ks_n = (KS_ALL - kb * 4) < 4 ? (KS_ALL - kb * 4) : 4;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < ks_n) umma_bf16(tmem + (b * TILES + t) * 64, ad + 2 * ks, bd + 2 * ks, idesc1, (kb | ks) != 0);
+              }
             }
+            umma_commit(bar(B_D1FULL + b));
+            if (c == NC - 1) umma_commit(bar(B_A1FREE + ab));
           }
-          umma_commit(bar(B_D1FULL + b));
-          if (c == NC - 1) umma_commit(bar(B_A1FREE + ab));
+          __syncwarp();
           T(2);
           if (u > 0) gemm2(u - 1);
         }

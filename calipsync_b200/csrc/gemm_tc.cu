@@ -30,15 +30,18 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kABytes = kBM * 128;   // 16 KiB: 128 rows x 128 B
 constexpr int kProducers = 256;      // 8 producer warps
-constexpr int kEpiWarps = 8;          // two warps per TMEM lane quarter, each owns half of the tile columns
+constexpr int kEpiWarps = 8;          // dedicated epilogue warps (the 8 producer warps join them when A is TMA-loaded)
 constexpr int kThreads = kProducers + 2 * 32 + kEpiWarps * 32;
 constexpr int kLag = 2;              // A stages in flight per producer thread before publishing
 
 template <int BN>
 struct Cfg {
   static constexpr int kStage = kABytes + BN * 128;
+  static constexpr int kExtra = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue vectors*/ +
+                                16384 /*epilogue store staging: 8 warps x 32 rows x 64 B*/;
   static constexpr int S = (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;   // 256:4  128:6  64:8  32:8
-  static constexpr int kSmem = S * kStage + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue vectors*/;
+  static constexpr int kSmem = S * kStage + kExtra;
+  static_assert(kSmem <= 232448, "shared memory overflow");
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
 };
@@ -90,18 +93,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
+  // developer timing: one thread per role accumulates cycles per activity slot
+  long long tmark = p.dbg ? clock64() : 0;
+  const long long tstart = tmark;
+  const bool timed = p.dbg && (tid == 256 || tid == 288 || tid == 320);
+  auto T = [&](int slot) {
+    if (timed) {
+      const long long now = clock64();
+      atomicAdd(p.dbg + slot, (unsigned long long)(now - tmark));
+      tmark = now;
+    }
+  };
   const int KB = (p.K + 63) >> 6;
   const int NT = p.N / BN, MT = (p.M + kBM - 1) / kBM;
   const int n_tiles = NT * MT;
+  // epilogue column groups (4 warps each, one per TMEM lane quarter).  Letting the idle producer warps of the
+  // TMA-loaded mode drain too (16 epilogue warps) was measured SLOWER: a warp's chunk is a serial latency chain
+  // (tcgen05.ld -> bias -> activation -> staging -> store), and the extra staging smem costs a pipeline stage.
+  const int ncg = BN >= 64 ? 2 : 1;
+  const int epi_n = ncg * 128;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full(s), p.amode == A_PLAIN ? 2 : kProducers + 1);   // PLAIN: the TMA thread + the B loader
+      mbar_init(full(s), p.amode == A_PLAIN ? 2 : kProducers + 1);   // PLAIN: the TMA lane + the B loader
       mbar_init(empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full(a), 1);
-      mbar_init(acc_empty(a), kEpiWarps * 32);
+      mbar_init(acc_empty(a), epi_n);
     }
     fence_mbar_init();
   }
@@ -116,19 +135,164 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   // weights are constant: the B loader (and the MMA issuer behind it) start at once; every role that reads or
   // writes an activation buffer first waits for the previous kernel of the stream
+  T(10);
   if (warp < 8 || warp >= 10) pdl_wait();
+  if (tid == 320) T(11);
+
+  // ======================================= epilogue (warps 10-17) =================================================
+  auto run_epilogue = [&](const int ew) {
+    // ======================================= epilogue warps ==========================================================
+    const int lg = warp & 3;                 // TMEM lane quarter this warp may access
+    const int cg = ew >> 2;                  // column group of this warp
+    if (cg >= ncg) return;
+    const int cols_per = BN / ncg;
+    // per-tile epilogue vectors (bias, residual scale, trailing BN) are staged in shared memory while the tile's
+    // main loop runs, double-buffered across tiles: [buffer][bias | rscale | post_scale | post_shift][256]
+    float* const evec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
+    const int et = ew * 32 + lane;
+    // Output rows go through a warp-private staging slab (32 rows x 64 B, 16-byte chunks XOR-swizzled by row pair) and
+    // leave as 8 rows x 64 contiguous bytes per store instruction: a thread owns one accumulator ROW, so storing
+    // straight from registers writes 32 half-filled sectors per instruction (measured: ~11k cycles per 128x256 tile).
+    uint8_t* const stg = smem_raw + (bar_base + 256 + 8192 - smem_u32(smem_raw)) + ew * 2048;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int ab = t & 1;
+      const int n0 = (tile % NT) * BN, m0 = (tile / NT) * kBM;
+      float* const ev = evec + (t & 1) * 1024;
+      if (et < BN) {
+        ev[et] = __ldg(p.bias + n0 + et);
+        if (p.res_pre) ev[256 + et] = __ldg(p.rscale + n0 + et);
+        if (p.post_scale) {
+          ev[512 + et] = __ldg(p.post_scale + n0 + et);
+          ev[768 + et] = __ldg(p.post_shift + n0 + et);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_n) : "memory");
+      T(7);
+      const int m = m0 + lg * 32 + lane;
+      const bool row_ok = m < p.M;
+      const int cbeg = cg * cols_per, cend = cbeg + cols_per;
+      // residual rows (a launch uses res_pre or res_post, never both): the first 32-column chunk is requested BEFORE
+      // waiting for the accumulator, so its latency hides behind the tile's main loop; later chunks are prefetched
+      // one chunk ahead, behind the TMEM load + arithmetic of the current chunk
+      const __nv_bfloat16* rsrc = p.res_pre ? p.res_pre + (size_t)m * p.ld_rpre : p.res_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
+      uint4 rnext[4];
+      auto fetch_res = [&](int c0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          rnext[g] = (rsrc && row_ok) ? *reinterpret_cast<const uint4*>(rsrc + n0 + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+      };
+      if (cbeg < cend) fetch_res(cbeg);
+      mbar_wait(acc_full(ab), (t >> 1) & 1);
+      T(8);
+      tc_fence_after();
+      const uint32_t trow = tmem + ab * C::kAccCols + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(trow + c0, acc);
+        uint4 rcur[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+        if (c0 + 32 < cend) fetch_res(c0 + 32);
+        tmem_ld_wait32(acc);
+        T(13);
+        if (row_ok) {
+          const int n = n0 + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {  // 8 columns per group -> one 16 B store
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
+            if (p.res_pre) {
+              const uint32_t* pr = &rcur[g].x;
+              const float4 s0 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g + 4);
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] += ss[2 * q] * bf16_lo(pr[q]);
+                v[2 * q + 1] += ss[2 * q + 1] * bf16_hi(pr[q]);
+              }
+            }
+            if (p.leaky) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
+            }
+            if (p.res_post) {
+              const uint32_t* pr = &rcur[g].x;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] += bf16_lo(pr[q]);
+                v[2 * q + 1] += bf16_hi(pr[q]);
+              }
+            }
+            if (p.post_scale) {
+              const float4 s0 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g);
+              const float4 t1 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g + 4);
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                v[q] = ss[q] * v[q] + tt[q];
+                v[q] = fmaxf(v[q], kLeaky * v[q]);
+              }
+            }
+            if (p.vt && n0 >= p.vt_col0) {   // transposed store of a value projection (see GemmArgs::vt)
+              const int frame = m / 100, key = m - frame * 100;
+              const int colv = n + 8 * g - p.vt_col0;   // j * 512 + channel
+              __nv_bfloat16* dst = p.vt + ((size_t)frame * 2048 + colv) * 128 + key;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) dst[q * 128] = __float2bfloat16_rn(v[q]);
+            } else {
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]);
+              o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]);
+              o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+          }
+        }
+        T(14);
+        if (!(p.vt && n0 >= p.vt_col0)) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + (lane >> 2), c = lane & 3;
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4));
+            const int ml = m0 + lg * 32 + rl;
+            if (ml < p.M) *reinterpret_cast<uint4*>(p.C + (size_t)ml * p.ldc + n0 + c0 + 8 * c) = o;
+          }
+          __syncwarp();
+        }
+        T(15);
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(ab));
+      T(9);
+    }
+  };
 
   if (warp < 8 && p.amode == A_PLAIN) {
-    // ======================================= A via TMA (one thread) ==================================================
-    if (tid == 0) {
+    // ======================================= A via TMA (one elected lane of warp 0) =================================
+    if (warp == 0) {
       int j = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = (tile / NT) * kBM;
         for (int kb = 0; kb < KB; ++kb, ++j) {
           const int s = j % S;
           mbar_wait(empty(s), ((j / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(full(s), kABytes);
-          tma_load_2d(base + s * C::kStage, &tmA, kb * 64, m0, full(s));
+          if (elect_one()) {   // one 2-D TMA tensor copy (box 64 x 128, rows beyond M zero-filled)
+            mbar_arrive_expect_tx(full(s), kABytes);
+            tma_load_2d(base + s * C::kStage, &tmA, kb * 64, m0, full(s));
+          }
+          __syncwarp();
         }
       }
     }
@@ -234,163 +398,61 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
     fence_proxy_async();
     for (int q = (j > kLag ? j - kLag : 0); q < j; ++q) mbar_arrive(full(q % S));
   } else if (warp == 8) {
-    // ======================================= B loader (one thread) ==================================================
-    if (lane == 0) {
+    // ======================================= B loader (one elected lane) =============================================
+    {
       int j = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int n0 = (tile % NT) * BN;
         for (int kb = 0; kb < KB; ++kb, ++j) {
           const int s = j % S;
           mbar_wait(empty(s), ((j / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(full(s), BN * 128);
-          bulk_g2s(base + s * C::kStage + kABytes, p.W + ((size_t)kb * p.N + n0) * 128, BN * 128, full(s));
+          T(2);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full(s), BN * 128);
+            bulk_g2s(base + s * C::kStage + kABytes, p.W + ((size_t)kb * p.N + n0) * 128, BN * 128, full(s));
+          }
+          __syncwarp();
+          T(3);
         }
       }
     }
   } else if (warp == 9) {
-    // ======================================= MMA issuer (one thread) ================================================
-    if (lane == 0) {
+    // ======================================= MMA issuer (one elected lane of a converged warp) ======================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       int j = 0, t = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int ab = t & 1;
         mbar_wait(acc_empty(ab), ((t >> 1) & 1) ^ 1);
+        T(4);
         tc_fence_after();
         const uint32_t d = tmem + ab * C::kAccCols;
         for (int kb = 0; kb < KB; ++kb, ++j) {
           const int s = j % S;
           mbar_wait(full(s), (j / S) & 1);
+          T(5);
           tc_fence_after();
           const uint32_t a_s = base + s * C::kStage;
           const uint64_t adesc = umma_desc_sw128(a_s), bdesc = umma_desc_sw128(a_s + kABytes);
-          int ksteps = (p.K - kb * 64 + 15) >> 4;
-          ksteps = ksteps > 4 ? 4 : ksteps;
-          for (int ks = 0; ks < ksteps; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kb | ks) != 0);
-          umma_commit(empty(s));
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kb | ks) != 0);
+            umma_commit(empty(s));
+            if (kb == KB - 1) umma_commit(acc_full(ab));
+          }
+          __syncwarp();
+          T(6);
         }
-        umma_commit(acc_full(ab));
       }
     }
   } else {
-    // ======================================= epilogue warps ==========================================================
-    const int lg = warp & 3;                 // TMEM lane quarter this warp may access
-    const int ch = (warp - 10) >> 2;         // which half of the tile's columns
-    // per-tile epilogue vectors (bias, residual scale, trailing BN) are staged in shared memory while the tile's
-    // main loop runs, double-buffered across tiles: [buffer][bias | rscale | post_scale | post_shift][256]
-    float* const evec = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw)));
-    const int et = tid - (kProducers + 64);
-    constexpr int HALF = BN >= 64 ? BN / 2 : BN;   // BN = 32: one chunk, second warp set idles
-    int t = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const int ab = t & 1;
-      const int n0 = (tile % NT) * BN, m0 = (tile / NT) * kBM;
-      float* const ev = evec + (t & 1) * 1024;
-      if (et < BN) {
-        ev[et] = __ldg(p.bias + n0 + et);
-        if (p.res_pre) ev[256 + et] = __ldg(p.rscale + n0 + et);
-        if (p.post_scale) {
-          ev[512 + et] = __ldg(p.post_scale + n0 + et);
-          ev[768 + et] = __ldg(p.post_shift + n0 + et);
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      mbar_wait(acc_full(ab), (t >> 1) & 1);
-      tc_fence_after();
-      const int m = m0 + lg * 32 + lane;
-      const bool row_ok = m < p.M;
-      const uint32_t trow = tmem + ab * C::kAccCols + ((uint32_t)(lg * 32) << 16);
-      const int cbeg = BN >= 64 ? ch * HALF : 0, cend = BN >= 64 ? cbeg + HALF : (ch == 0 ? BN : 0);
-      // residual rows are prefetched one 32-column chunk ahead so their global-memory latency hides behind the
-      // TMEM load + arithmetic of the current chunk
-      // (a launch uses res_pre or res_post, never both)
-      const __nv_bfloat16* rsrc = p.res_pre ? p.res_pre + (size_t)m * p.ld_rpre : p.res_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
-      uint4 rnext[4];
-      auto fetch_res = [&](int c0) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          rnext[g] = (rsrc && row_ok) ? *reinterpret_cast<const uint4*>(rsrc + n0 + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
-      };
-      if (cbeg < cend) fetch_res(cbeg);
-#pragma unroll 1
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(trow + c0, acc);
-        uint4 rcur[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-        if (c0 + 32 < cend) fetch_res(c0 + 32);
-        tmem_ld_wait32(acc);
-        if (row_ok) {
-          const int n = n0 + c0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 8 columns per group -> one 16 B store
-            float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g);
-            const float4 b1 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
-            if (p.res_pre) {
-              const uint32_t* pr = &rcur[g].x;
-              const float4 s0 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g);
-              const float4 s1 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g + 4);
-              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[2 * q] += ss[2 * q] * bf16_lo(pr[q]);
-                v[2 * q + 1] += ss[2 * q + 1] * bf16_hi(pr[q]);
-              }
-            }
-            if (p.leaky) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
-            }
-            if (p.res_post) {
-              const uint32_t* pr = &rcur[g].x;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[2 * q] += bf16_lo(pr[q]);
-                v[2 * q + 1] += bf16_hi(pr[q]);
-              }
-            }
-            if (p.post_scale) {
-              const float4 s0 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g);
-              const float4 s1 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g + 4);
-              const float4 t0 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g);
-              const float4 t1 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g + 4);
-              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-              const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                v[q] = ss[q] * v[q] + tt[q];
-                v[q] = fmaxf(v[q], kLeaky * v[q]);
-              }
-            }
-            if (p.vt && n0 >= p.vt_col0) {   // transposed store of a value projection (see GemmArgs::vt)
-              const int frame = m / 100, key = m - frame * 100;
-              const int colv = n + 8 * g - p.vt_col0;   // j * 512 + channel
-              __nv_bfloat16* dst = p.vt + ((size_t)frame * 2048 + colv) * 128 + key;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) dst[q * 128] = __float2bfloat16_rn(v[q]);
-            } else {
-              uint4 o;
-              o.x = pack_bf16(v[0], v[1]);
-              o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]);
-              o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.C + (size_t)m * p.ldc + n + 8 * g) = o;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(acc_empty(ab));
-    }
+    run_epilogue(warp - 10);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, C::kTmemCols);
+  if (p.dbg && tid == 0) atomicAdd(p.dbg + 12, (unsigned long long)(clock64() - tstart));
 }
 
 int g_num_sms = 148;
@@ -460,7 +522,7 @@ int gemm_init() {
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
-  if (a.N % 32 != 0 || a.K % 8 != 0) return (int)cudaErrorInvalidValue;
+  if (a.N % 32 != 0 || a.K % 64 != 0) return (int)cudaErrorInvalidValue;   // whole 64-channel k-blocks only
   const long mt = (a.M + kBM - 1) / kBM;
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   int best = 32;

@@ -33,6 +33,7 @@ struct GemmArgs {
   // can use V^T as a K-major B operand of tcgen05.mma (module/unet.py:215: out = V . attn^T)
   __nv_bfloat16* vt;
   int vt_col0;
+  unsigned long long* dbg;  // developer timing (CASYNC_GEMM_DBG=<label substring>): per-role cycle counters [16]
 };
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);  // returns 0 or cudaError

@@ -144,14 +144,17 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
   fence_proxy_async();
   __syncthreads();
   // ---- pw2 on the tensor core: D[tile] = A2[tile] (128 x 16) . W2^T (16 x 32)
-  if (tid == 0) {
+  if (warp == 0) {
     mbar_wait(bar_w, 0);
     tc_fence_after();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
-    const uint64_t bdesc = umma_desc_sw128(smem_u32(s.w2));
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
+      const uint64_t bdesc = umma_desc_sw128(smem_u32(s.w2));
 #pragma unroll
-    for (int t = 0; t < 2; ++t) umma_bf16(tmem + t * 32, umma_desc_sw128(smem_u32(s.a2[t])), bdesc, idesc, 0);
-    umma_commit(bar_mma);
+      for (int t = 0; t < 2; ++t) umma_bf16(tmem + t * 32, umma_desc_sw128(smem_u32(s.a2[t])), bdesc, idesc, 0);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
   }
   // ---- epilogue: TMEM -> +bias, leaky -> bf16 NHWC (64 B per pixel)
   mbar_wait(bar_mma, 0);
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(const __nv_bfloat16* 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s.tmem_slot;
-  if (tid == 0) {   // S[128 x 112] = Q K^T
+  if (warp == 4 && elect_one()) {   // S[128 x 112] = Q K^T   (warp 4: converged here, not part of the softmax group)
     constexpr uint32_t idesc = umma_idesc_bf16(128, 112);
     const uint64_t ad = umma_desc_sw128(sq), bd = umma_desc_sw128(sk);
 #pragma unroll
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(256, 1) attention_kernel(const __nv_bfloat16* 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) {   // O[128 x 256] = P V  (K = 112 keys: 4 + 3 steps of 16)
+  if (warp == 4 && elect_one()) {   // O[128 x 256] = P V  (K = 112 keys: 4 + 3 steps of 16)
     constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
 #pragma unroll
     for (int ks = 0; ks < 7; ++ks) {

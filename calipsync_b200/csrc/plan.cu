@@ -34,7 +34,12 @@ struct Prof {
   std::vector<casync_launch_record> recs;
 };
 thread_local Prof* g_prof = nullptr;
-thread_local int g_cap = 0;   // CTA cap of persistent kernels while two branches of the forward share the GPU
+thread_local int g_cap = 0;
+unsigned long long* g_gemm_dbg = nullptr;   // developer timing of the GEMM roles (CASYNC_GEMM_DBG=<label substring>)
+std::string g_gemm_dbg_match;
+unsigned long long* gemm_dbg_for(const std::string& label) {
+  return g_gemm_dbg && label.find(g_gemm_dbg_match) != std::string::npos ? g_gemm_dbg : nullptr;
+}   // CTA cap of persistent kernels while two branches of the forward share the GPU
 void prof_mark(const char* label, double flops, double bytes) {
   if (!g_prof) return;
   casync_launch_record r{};
@@ -273,6 +278,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g.C = h1;
   g.ldc = hid;
   g.max_ctas = g_cap;
+  g.dbg = gemm_dbg_for(short_name(d.name) + ".pw1");
   if (up_low) {
     g.amode = A_UPCAT;
     g.A = up_low;
@@ -309,6 +315,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.C = out;
   g2.ldc = ldc;
   g2.max_ctas = g_cap;
+  g2.dbg = gemm_dbg_for(short_name(d.name) + ".pw2");
   CK(launch_gemm(g2, st));
   prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
   return 0;
@@ -334,6 +341,7 @@ int run_dense(const casync_plan* p, const char* wname, const char* bname, const 
   g.C = C;
   g.ldc = ldc;
   g.max_ctas = g_cap;
+  g.dbg = gemm_dbg_for(wname);
   CK(launch_gemm(g, st));
   prof_mark(wname, 2.0 * M * K * N, 2.0 * M * (K + N * (res_pre ? 2 : 1)));
   return 0;
@@ -552,6 +560,10 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
     p->phase_dbg_ir = atoi(c);
     if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
   }
+  if (const char* c = getenv("CASYNC_GEMM_DBG")) {
+    g_gemm_dbg_match = c;
+    if (cudaMalloc(&g_gemm_dbg, 128) == cudaSuccess) cudaMemset(g_gemm_dbg, 0, 128);
+  }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
   if (const char* c = getenv("CASYNC_OVERLAP")) p->overlap = atoi(c) > 0;          // A/B switch for the two-stream overlap
@@ -589,6 +601,19 @@ void casync_plan_destroy(casync_plan* plan) {
       fprintf(stderr, "  [%.3g cycles]\n", tot);
     }
     cudaFree(plan->phase_dbg);
+  }
+  if (plan && g_gemm_dbg) {
+    unsigned long long h[16] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, g_gemm_dbg, 128, cudaMemcpyDeviceToHost);
+    const char* names[16] = {"A:wait_empty", "A:issue", "B:wait_empty", "B:issue", "M:wait_acc_empty", "M:wait_full",
+                             "M:issue", "E:stage_vec", "E:wait_acc_full", "E:tail", "all:prologue", "pdl_wait",
+                             "cta_total", "E:tmem_ld", "E:math_sts", "E:store"};
+    fprintf(stderr, "[casync gemm dbg] '%s' (cycles summed over CTAs and launches):\n   ", g_gemm_dbg_match.c_str());
+    for (int i = 0; i < 16; ++i) fprintf(stderr, " %s=%.3g", names[i], (double)h[i]);
+    fprintf(stderr, "\n");
+    cudaFree(g_gemm_dbg);
+    g_gemm_dbg = nullptr;
   }
   if (plan) {
     if (plan->side) {
