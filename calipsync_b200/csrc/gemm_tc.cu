@@ -43,7 +43,8 @@ struct Cfg {
   static constexpr int kSmem = S * kStage + kExtra;
   static_assert(kSmem <= 232448, "shared memory overflow");
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
-  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
+                                   : 2 * kAccCols <= 256 ? 256 : 512;   // tcgen05.alloc wants a power of two
 };
 
 struct RowCoord {  // UPCAT per-thread bilinear taps
@@ -516,6 +517,7 @@ int gemm_init() {
   e |= set_attr<32>();
   e |= set_attr<64>();
   e |= set_attr<128>();
+  e |= set_attr<192>();
   e |= set_attr<256>();
   return e;
 }
@@ -527,7 +529,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   int best = 32;
   double bc = tile_cost(mt, a.N, 32, cap);
-  for (int bn : {64, 128, 256}) {
+  for (int bn : {64, 128, 192, 256}) {   // 192: N = 576 (p_1 + q) -> 3 column tiles instead of 9
+    if (a.vt && a.vt_col0 % bn) continue;   // a column tile must not straddle the row-major | transposed boundary
     const double c = tile_cost(mt, a.N, bn, cap);
     if (c <= bc) {
       bc = c;
@@ -536,6 +539,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   switch (best) {
     case 256: return launch_cfg<256>(a, stream);
+    case 192: return launch_cfg<192>(a, stream);
     case 128: return launch_cfg<128>(a, stream);
     case 64: return launch_cfg<64>(a, stream);
     default: return launch_cfg<32>(a, stream);
