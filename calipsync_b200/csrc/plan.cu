@@ -193,8 +193,11 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
-  bool overlap = false;             // CASYNC_OVERLAP=1: audio encoder on a side stream next to the low-resolution face
-                                    // encoder (measured: no gain at batch 64 -- both branches are wave-bound, not idle)
+  bool overlap = true;              // audio encoder on a side stream next to the low-resolution face encoder, for
+  int overlap_max_batch = 32;       // small batches only (measured: +10 % at batch 8, nothing at batch 64 where both
+                                    // branches are wave-bound, not idle).  CASYNC_OVERLAP=0|1|2 forces it off / on / on
+                                    // without CTA caps.
+  bool overlap_cap = true;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
@@ -459,7 +462,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   // The audio encoder (and the key/value GEMM behind it) is independent of the face encoder.  Its kernels and the
   // low-resolution half of the face encoder are both latency-bound at small batch, so they run side by side: the
   // audio branch on the plan's side stream, each branch's persistent kernels capped to half of the SMs.
-  const bool overlap = p->overlap && p->side && !g_prof;
+  const bool overlap = p->overlap && p->side && !g_prof && batch <= p->overlap_max_batch;
   auto down_block = [&](int l) -> int {
     const int i0 = IR_DOWN + 2 * l;
     int e2;
@@ -475,7 +478,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     if ((e = run_ir(p, i0, cur, nullptr, w[dn_t[1]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
     CK(cudaEventRecord(p->ev_fork, st));
     CK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-    g_cap = p->num_sms / 2;
+    g_cap = p->overlap_cap ? p->num_sms / 2 : 0;
     e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, p->side);
     if (!e) e = run_kv(p, w["cat"], w, batch, p->side);
     if (!e) e = run_ir(p, i0 + 1, w[dn_t[1]], nullptr, w[dn_o[1]], kIr[i0 + 1].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st);
@@ -566,7 +569,11 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
-  if (const char* c = getenv("CASYNC_OVERLAP")) p->overlap = atoi(c) > 0;          // A/B switch for the two-stream overlap
+  if (const char* c = getenv("CASYNC_OVERLAP")) {   // A/B switch for the two-stream overlap (2: no CTA caps)
+    p->overlap = atoi(c) > 0;
+    p->overlap_cap = atoi(c) == 1;
+    p->overlap_max_batch = 1 << 30;
+  }
   if (p->overlap) {
     if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
