@@ -25,6 +25,10 @@ inline bool& pdl_enabled() {
   static bool on = true;
   return on;
 }
+inline long& launch_counter() {   // kernels launched by this thread (casync_launches_per_forward reports measured counts)
+  static thread_local long n = 0;
+  return n;
+}
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {
@@ -38,6 +42,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  ++launch_counter();
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 

@@ -17,6 +17,7 @@
 //                            main loop of the CTA's next tile.
 // Grid = min(#tiles, #SMs); tiles are walked N-fastest so CTAs that share an A tile run at the same time.
 #include "gemm_tc.cuh"
+#include "gemm_dev.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -46,38 +47,6 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
                                    : 2 * kAccCols <= 256 ? 256 : 512;   // tcgen05.alloc wants a power of two
 };
-
-struct RowCoord {  // UPCAT per-thread bilinear taps
-  const __nv_bfloat16 *p00, *p01, *p10, *p11;
-  float wy0, wy1, wx0, wx1;
-};
-
-__device__ __forceinline__ uint4 lerp8(const uint4& a, const uint4& b, const uint4& c, const uint4& d,
-                                       const RowCoord& rc) {
-  const uint32_t* pa = &a.x;
-  const uint32_t* pb = &b.x;
-  const uint32_t* pc = &c.x;
-  const uint32_t* pd = &d.x;
-  uint4 o;
-  uint32_t* po = &o.x;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    // same association as PyTorch's upsample_bilinear2d: wy0*(wx0*p00 + wx1*p01) + wy1*(wx0*p10 + wx1*p11)
-    float lo = rc.wy0 * (rc.wx0 * bf16_lo(pa[i]) + rc.wx1 * bf16_lo(pb[i])) +
-               rc.wy1 * (rc.wx0 * bf16_lo(pc[i]) + rc.wx1 * bf16_lo(pd[i]));
-    float hi = rc.wy0 * (rc.wx0 * bf16_hi(pa[i]) + rc.wx1 * bf16_hi(pb[i])) +
-               rc.wy1 * (rc.wx0 * bf16_hi(pc[i]) + rc.wx1 * bf16_hi(pd[i]));
-    po[i] = pack_bf16(lo, hi);
-  }
-  return o;
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
@@ -463,6 +432,27 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
+}  // namespace
+
+int gemm_encode_map(void* tm_out, const __nv_bfloat16* A, int rows, int cols, int ld, int box_rows, bool swizzle128) {
+  // [rows, cols] bf16 row-major with pitch ld: box = 64 columns (128 B) x box_rows rows; rows outside are zero-filled
+  if (!g_encode || (ld & 7) || ((uintptr_t)A & 15) || box_rows < 1 || box_rows > 256) return (int)cudaErrorInvalidValue;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  if (g_encode(reinterpret_cast<CUtensorMap*>(tm_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(A),
+               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  return 0;
+}
+
+int gemm_num_sms() { return g_num_sms; }
+
+namespace {
+
 template <int BN>
 int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   const int tiles = (a.N / BN) * ((a.M + kBM - 1) / kBM);
@@ -472,15 +462,8 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   memset(&tm, 0, sizeof tm);
   if (a.amode == A_PLAIN) {
     // A[M, K] bf16 row-major with pitch lda: box = 64 columns (128 B, one swizzle span) x 128 rows
-    if (!g_encode || (a.lda & 7) || ((uintptr_t)a.A & 15)) return (int)cudaErrorInvalidValue;
-    const cuuint64_t gdim[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
-    const cuuint64_t gstride[1] = {(cuuint64_t)a.lda * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)kBM};
-    const cuuint32_t estr[2] = {1, 1};
-    if (g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a.A), gdim, gstride, box, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return (int)cudaErrorInvalidValue;
+    const int e = gemm_encode_map(&tm, a.A, a.M, a.K, a.lda, kBM, true);
+    if (e) return e;
   }
   return (int)launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, stream, a, tm);
 }

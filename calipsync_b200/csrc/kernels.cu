@@ -190,9 +190,8 @@ constexpr int kDwSmemMax = 56 * 1024;
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
-                                                    __nv_bfloat16* __restrict__ out, const float* __restrict__ wd,
-                                                    const float* __restrict__ bd, int H, int W, int C, int Ho,
-                                                    int Wo, int BR) {
+                                                    __nv_bfloat16* __restrict__ out, const uint4* __restrict__ wdp,
+                                                    int H, int W, int C, int Ho, int Wo, int BR) {
   extern __shared__ uint4 dw_tile[];   // [rows_in][W + 2][8 chunks of 8 channels]
   pdl_launch_dependents();
   const int tid = threadIdx.x, chunk = tid & 7;
@@ -200,25 +199,15 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
   const int rows_out = BR < Ho - oy0 ? BR : Ho - oy0;
   const int rows_in = (rows_out - 1) * STRIDE + 3, TW = W + 2;
   const int iy0 = oy0 * STRIDE - 1;
-  // taps / bias of this thread's 8 channels (constants: fetched before waiting for the previous kernel)
+  // taps / bias of this thread's 8 channels, packed bf16 [C/8][10][8] (constants: fetched before waiting for the
+  // previous kernel): ten 16-byte loads, no conversions
   const int c = c0 + chunk * 8;
-  __nv_bfloat162 wt[9][4], wb[4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wd + t * C + c));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wd + t * C + c + 4));
-    wt[t][0] = __floats2bfloat162_rn(w0.x, w0.y);
-    wt[t][1] = __floats2bfloat162_rn(w0.z, w0.w);
-    wt[t][2] = __floats2bfloat162_rn(w1.x, w1.y);
-    wt[t][3] = __floats2bfloat162_rn(w1.z, w1.w);
-  }
+  uint4 wt[9], wb;
   {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bd + c));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bd + c + 4));
-    wb[0] = __floats2bfloat162_rn(b0.x, b0.y);
-    wb[1] = __floats2bfloat162_rn(b0.z, b0.w);
-    wb[2] = __floats2bfloat162_rn(b1.x, b1.y);
-    wb[3] = __floats2bfloat162_rn(b1.z, b1.w);
+    const uint4* tp = wdp + (size_t)(c >> 3) * 10;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = __ldg(tp + t);
+    wb = __ldg(tp + 9);
   }
   const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
   pdl_wait();   // the hidden tensor is the previous kernel's output
@@ -239,15 +228,18 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
   for (int p = tid >> 3; p < nunits; p += 32) {
     const int oy = p / Wo, ox = p - oy * Wo;
     const uint4* t0 = dw_tile + ((oy * STRIDE) * TW + ox * STRIDE) * 8 + chunk;
-    __nv_bfloat162 a[4] = {wb[0], wb[1], wb[2], wb[3]};
+    __nv_bfloat162 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = reinterpret_cast<const __nv_bfloat162*>(&wb)[q];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const uint4 v = t0[(ky * TW + kx) * 8];
         const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&wt[ky * 3 + kx]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = __hfma2(wt[ky * 3 + kx][q], pv[q], a[q]);
+        for (int q = 0; q < 4; ++q) a[q] = __hfma2(pw[q], pv[q], a[q]);
       }
     uint4 o;
     __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -558,9 +550,9 @@ int launch_inc(const float* x, __nv_bfloat16* out, const uint8_t* w2t, const Inc
   return (int)launch_pdl(inc_kernel, grid, dim3(256), sizeof(IncSmem) + 1024, st, x, out, w2t, w);
 }
 
-int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
-                 int W, int C, int stride, cudaStream_t st) {
-  if (C % 64 != 0 || (stride != 1 && stride != 2)) return (int)cudaErrorInvalidValue;
+int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp, int batch, int H, int W, int C,
+                 int stride, cudaStream_t st) {
+  if (C % 64 != 0 || (stride != 1 && stride != 2) || !wdp || ((uintptr_t)wdp & 15)) return (int)cudaErrorInvalidValue;
   const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
   // rows per band: the input band (BR*stride + 2 rows of (W+2) pixels x 128 B) must fit the smem budget
   const int row_bytes = (W + 2) * 128;
@@ -571,8 +563,9 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, c
   BR = (Ho + bands - 1) / bands;   // balance the bands
   const size_t smem = (size_t)((BR - 1) * stride + 3) * row_bytes;
   const dim3 grid((unsigned)(C / 64), (unsigned)bands, (unsigned)batch);
-  if (stride == 2) return (int)launch_pdl(dw3x3_kernel<2>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
-  return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, wd, bd, H, W, C, Ho, Wo, BR);
+  const uint4* taps = reinterpret_cast<const uint4*>(wdp);
+  if (stride == 2) return (int)launch_pdl(dw3x3_kernel<2>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR);
+  return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR);
 }
 
 int launch_prepare_inputs(const uint8_t* crops, const float* feats, int T, const int* frame_idx, float* x, float* audio,

@@ -23,9 +23,10 @@ struct OutcParams {   // OutConv + outc_bn folded (module/unet.py:100-106, 342-3
 
 int launch_inc(const float* x_nchw, __nv_bfloat16* x1_nhwc, const uint8_t* w2_tile, const IncParams& w, int batch,
                cudaStream_t st);
-// depthwise 3x3, pad 1, stride 1|2, + folded BN bias + LeakyReLU.  NHWC bf16 -> NHWC bf16, wd fp32 [9][C].
-int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const float* wd, const float* bd, int batch, int H,
-                 int W, int C, int stride, cudaStream_t st);
+// depthwise 3x3, pad 1, stride 1|2, + folded BN bias + LeakyReLU.  NHWC bf16 -> NHWC bf16; wdp: taps + bias as bf16,
+// [C/8][10][8] (9 taps, then the bias, per 8-channel chunk).
+int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp, int batch, int H, int W, int C,
+                 int stride, cudaStream_t st);
 // caller-side input assembly on the device: uint8 HWC crops -> x [B,6,160,160] (reference face + masked face, /255)
 // and HuBERT features [T,2,1024] + frame indices -> audio windows [B,32,32,32] (infer_api.py:99-145, 238-245)
 int launch_prepare_inputs(const uint8_t* crops, const float* feats, int T, const int* frame_idx, float* x, float* audio,

@@ -77,7 +77,14 @@ def build_entries(sd):
 
     for name, _ in _lib.weight_schema():
         prefix, part = name.split("|")
-        if part in ("w1", "b1", "wd", "bd", "w2", "b2"):
+        if part == "wdp":
+            # depthwise taps + folded-BN bias as bf16, [hid/8][10][8]: the 64-channel slice a depthwise work item of
+            # the layer-program kernel handles is 1280 contiguous bytes (one bulk copy next to its slab of hidden rows)
+            _, _, wd, bd, _, _ = ir_parts(prefix)
+            hid = wd.shape[1]
+            t = torch.cat([wd, bd[None, :]], 0).view(10, hid // 8, 8).permute(1, 0, 2).contiguous()
+            val = t.float().to(torch.bfloat16).view(torch.uint8).numpy().reshape(-1).copy()   # same two roundings as the fp32 taps
+        elif part in ("w1", "b1", "wd", "bd", "w2", "b2"):
             w1, b1, wd, bd, w2, b2 = ir_parts(prefix)
             val = {"w1": lambda: pack_gemm_weight(w1), "b1": lambda: _f32(b1), "wd": lambda: _f32(wd),
                    "bd": lambda: _f32(bd), "w2": lambda: pack_gemm_weight(w2), "b2": lambda: _f32(b2)}[part]()

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> blob(total, 0);
   for (int i = 0; i < n; ++i) {
     const std::string part = names[i].substr(names[i].find('|') + 1);
-    const bool is_bf16 = part == "w1" || part == "w2" || part == "w" || part == "kv_w" || part == "p1q_w" || part == "b1_w" || part == "w2t";
+    const bool is_bf16 = part == "w1" || part == "w2" || part == "w" || part == "kv_w" || part == "p1q_w" || part == "b1_w" || part == "w2t" || part == "wdp";
     if (is_bf16) {
       uint16_t* p = reinterpret_cast<uint16_t*>(blob.data() + off[i]);
       for (size_t j = 0; j < sizes[i] / 2; ++j) p[j] = f2bf(0.03f * frand());
@@ -64,6 +64,24 @@ int main(int argc, char** argv) {
       const float scale = (part == "rs" || part == "b1_rs" || part == "s") ? 1.0f : 0.1f;
       for (size_t j = 0; j < sizes[i] / 4; ++j) p[j] = scale == 1.0f ? 1.0f + 0.1f * frand() : scale * frand();
     }
+  }
+  // the packed bf16 depthwise taps ("wdp", [hid/8][10][8]) must agree with the fp32 taps / bias ("wd" [9][hid], "bd")
+  for (int i = 0; i < n; ++i) {
+    const size_t bar = names[i].find('|');
+    if (names[i].substr(bar + 1) != "wdp") continue;
+    const std::string pre = names[i].substr(0, bar + 1);
+    int iwd = -1, ibd = -1;
+    for (int k = 0; k < n; ++k) {
+      if (names[k] == pre + "wd") iwd = k;
+      if (names[k] == pre + "bd") ibd = k;
+    }
+    const int hid = (int)(sizes[i] / 20);
+    const float* wd = reinterpret_cast<const float*>(blob.data() + off[iwd]);
+    const float* bd = reinterpret_cast<const float*>(blob.data() + off[ibd]);
+    uint16_t* o = reinterpret_cast<uint16_t*>(blob.data() + off[i]);
+    for (int c = 0; c < hid / 8; ++c)
+      for (int t = 0; t < 10; ++t)
+        for (int e = 0; e < 8; ++e) o[(c * 10 + t) * 8 + e] = f2bf(t < 9 ? wd[t * hid + c * 8 + e] : bd[c * 8 + e]);
   }
   void* dblob;
   CK(cudaMalloc(&dblob, total));
@@ -115,6 +133,33 @@ int main(int argc, char** argv) {
   const double host_ms = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / iters;
   printf("batch %d: %.4f ms/forward -> %.0f frames/s  (%lld launches/forward, host enqueue %.3f ms/forward, workspace %.1f MB)\n",
          B, ms / iters, B * iters / (ms * 1e-3), (long long)casync_launches_per_forward(plan, B), host_ms, wsb / 1e6);
+  {   // FNV-1a of the last output: lets two runs (e.g. CASYNC_NO_CHAIN=0|1) be compared bit for bit
+    const size_t ob = (size_t)B * 76800 * ((flags & CASYNC_F_OUT_U8_HWC) ? 1 : 4);
+    std::vector<uint8_t> ho(ob);
+    CK(cudaMemcpy(ho.data(), out, ob, cudaMemcpyDeviceToHost));
+    uint64_t h = 1469598103934665603ull;
+    double sum = 0;
+    for (size_t i = 0; i < ob; ++i) h = (h ^ ho[i]) * 1099511628211ull;
+    if (!(flags & CASYNC_F_OUT_U8_HWC))
+      for (size_t i = 0; i < ob / 4; ++i) sum += reinterpret_cast<const float*>(ho.data())[i];
+    printf("output hash %016llx  mean %.6f\n", (unsigned long long)h, sum / (ob / 4.0));
+    if (const char* dump = getenv("CASYNC_DUMP_WS")) {   // whole workspace (stage buffers), for bisecting a mismatch
+      std::vector<uint8_t> hw(wsb);
+      CK(cudaMemcpy(hw.data(), ws, wsb, cudaMemcpyDeviceToHost));
+      FILE* f = fopen(dump, "wb");
+      if (f) {
+        fwrite(hw.data(), 1, wsb, f);
+        fclose(f);
+      }
+    }
+    if (const char* dump = getenv("CASYNC_DUMP")) {
+      FILE* f = fopen(dump, "wb");
+      if (f) {
+        fwrite(ho.data(), 1, ob, f);
+        fclose(f);
+      }
+    }
+  }
   if (profile) {
     std::vector<casync_launch_record> recs(1024);
     std::vector<double> acc;
