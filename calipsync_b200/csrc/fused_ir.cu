@@ -43,7 +43,11 @@ constexpr int kIssuerWarp = (2 * kGroup + kProd) / 32;
 constexpr int kThreads = 2 * kGroup + kProd + 32;   // group B + group A + producers + issuer warp
 constexpr int kTile = 128 * 128;            // bytes of one 128-row x 128 B swizzled tile
 
-template <int CIN, int COUT, int STRIDE, int TILES, int A1BUFS>
+// WS ("weight streaming"): W1 / W2 do not stay resident -- the 64-row slice of W1 and the k-block of W2 that one unit
+// (patch x hidden chunk) needs are fetched into two-deep rings by the MMA issuer, one unit ahead, so blocks with
+// CIN >= 128 (down2.1: 128 KB of weights, up2.0: 320 KB) fit.  The depthwise taps then come pre-packed as bf16
+// ([CH/8][10][8], the layout of the stand-alone depthwise kernel) to save 13 bytes of shared memory per channel.
+template <int CIN, int COUT, int STRIDE, int TILES, int A1BUFS, bool WS = false>
 struct FCfg {
   static constexpr int CH = 2 * CIN, NC = CH / 64, KB1 = (CIN + 63) / 64;
   static constexpr int WIN_H = 8 * TILES;
@@ -55,15 +59,17 @@ struct FCfg {
   static constexpr int oA1 = 0;
   static constexpr int oHID = oA1 + A1BUFS * kA1Buf;
   static constexpr int oA2 = oHID + 2 * kHidBuf;
+  static constexpr int kW1Chunk = KB1 * 64 * 128, kW2Chunk = COUT * 128;   // what one unit reads of W1 / W2
   static constexpr int oW1 = oA2 + 2 * kA2Buf;
-  static constexpr int oW2 = oW1 + KB1 * CH * 128;
-  static constexpr int oWD = oW2 + NC * COUT * 128;
-  static constexpr int oB1 = oWD + 9 * CH * 4;
+  static constexpr int oW2 = oW1 + (WS ? 2 * kW1Chunk : KB1 * CH * 128);
+  static constexpr int oWD = oW2 + (WS ? 2 * kW2Chunk : NC * COUT * 128);
+  static constexpr int oB1 = oWD + (WS ? CH * 20 : 9 * CH * 4);
   static constexpr int oBD = oB1 + CH * 4;
-  static constexpr int oB2 = oBD + CH * 4;
+  static constexpr int oB2 = oBD + (WS ? 0 : CH * 4);
   static constexpr int oBAR = oB2 + COUT * 4;
   static constexpr int kSmem = oBAR + 256 + 1024;
-  static constexpr uint32_t kWeightBytes = KB1 * CH * 128 + NC * COUT * 128 + 9 * CH * 4 + 2 * CH * 4 + COUT * 4;
+  static constexpr uint32_t kWeightBytes =
+      WS ? CH * 20 + CH * 4 + COUT * 4 : KB1 * CH * 128 + NC * COUT * 128 + 9 * CH * 4 + 2 * CH * 4 + COUT * 4;
   static constexpr int kTmemD2 = 2 * TILES * 64;   // D1 double buffer first, then D2
   static_assert(kTmemD2 + A2T * COUT <= 512, "TMEM overflow");
   static_assert(kSmem <= 232448, "shared memory overflow");
@@ -71,7 +77,7 @@ struct FCfg {
 
 enum Bar : int {
   B_W = 0, B_A1FULL = 1, B_A1FREE = 3, B_D1FULL = 5, B_D1FREE = 7, B_HIDFULL = 9, B_HIDFREE = 11, B_A2FULL = 13,
-  B_A2FREE = 15, B_D2FULL = 17, B_D2FREE = 18, B_COUNT = 19
+  B_A2FREE = 15, B_D2FULL = 17, B_D2FREE = 18, B_W1FULL = 19, B_W1FREE = 21, B_W2FULL = 23, B_W2FREE = 25, B_COUNT = 27
 };
 
 // Shared-memory accesses of the CUDA-core phases are ordinary C++ loads/stores (through the generic pointer of
@@ -88,9 +94,9 @@ struct Patch {
   int b, OY0, OX0, GY0, GX0;
 };
 
-template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS>
+template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS, bool WS>
 __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p) {
-  using C = FCfg<CIN, COUT, STRIDE, TILES, A1BUFS>;
+  using C = FCfg<CIN, COUT, STRIDE, TILES, A1BUFS, WS>;
   constexpr int CH = C::CH, NC = C::NC, KB1 = C::KB1, TOH = C::TOH, TOW = C::TOW, NOUT = C::NOUT, A2T = C::A2T;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -123,13 +129,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     }
     mbar_init(bar(B_D2FULL), 1);
     mbar_init(bar(B_D2FREE), kGroup);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_W1FULL + i), 1);
+      mbar_init(bar(B_W1FREE + i), 1);
+      mbar_init(bar(B_W2FULL + i), 1);
+      mbar_init(bar(B_W2FREE + i), 1);
+    }
     fence_mbar_init();
     mbar_arrive_expect_tx(bar(B_W), C::kWeightBytes);
-    bulk_g2s(sW1, p.W1, KB1 * CH * 128, bar(B_W));
-    bulk_g2s(sW2, p.W2, NC * COUT * 128, bar(B_W));
-    bulk_g2s(sWD, p.wd, 9 * CH * 4, bar(B_W));
+    if constexpr (WS) {
+      bulk_g2s(sWD, p.wdp, CH * 20, bar(B_W));
+    } else {
+      bulk_g2s(sW1, p.W1, KB1 * CH * 128, bar(B_W));
+      bulk_g2s(sW2, p.W2, NC * COUT * 128, bar(B_W));
+      bulk_g2s(sWD, p.wd, 9 * CH * 4, bar(B_W));
+      bulk_g2s(sBD, p.bd, CH * 4, bar(B_W));
+    }
     bulk_g2s(sB1, p.b1, CH * 4, bar(B_W));
-    bulk_g2s(sBD, p.bd, CH * 4, bar(B_W));
     bulk_g2s(sB2, p.b2, COUT * 4, bar(B_W));
   }
   if (warp == kIssuerWarp) {
@@ -178,14 +194,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     // the whole (converged) warp walks the schedule and waits; one elected lane issues the tcgen05 instructions
     if (n_mine > 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64), idesc2 = umma_idesc_bf16(128, COUT);
+      // weight streaming: unit v's slice of W1 (needed by its first GEMM) and k-block of W2 (second GEMM) go to ring
+      // slot v & 1; a slot is refilled once the MMAs of unit v - 2 that read it have completed (tcgen05.commit)
+      auto load_w1 = [&](int v) {
+        const int cv = v % NC, b = v & 1, k = v >> 1;
+        mbar_wait(bar(B_W1FREE + b), (k & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar(B_W1FULL + b), C::kW1Chunk);
+#pragma unroll
+          for (int kb = 0; kb < KB1; ++kb)
+            bulk_g2s(sW1 + b * C::kW1Chunk + kb * 64 * 128, p.W1 + ((size_t)kb * CH + cv * 64) * 128, 64 * 128, bar(B_W1FULL + b));
+        }
+        __syncwarp();
+      };
+      auto load_w2 = [&](int v) {
+        const int cv = v % NC, b = v & 1, k = v >> 1;
+        mbar_wait(bar(B_W2FREE + b), (k & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar(B_W2FULL + b), C::kW2Chunk);
+          bulk_g2s(sW2 + b * C::kW2Chunk, p.W2 + (size_t)cv * COUT * 128, C::kW2Chunk, bar(B_W2FULL + b));
+        }
+        __syncwarp();
+      };
       auto gemm2 = [&](int v) {   // D2[patch] (+)= A2[v] . W2[:, chunk]^T
         const int pv = v / NC, cv = v - pv * NC, b = v & 1, k = v >> 1;
         mbar_wait(bar(B_A2FULL + b), k & 1);
         if (cv == 0) mbar_wait(bar(B_D2FREE), (pv & 1) ^ 1);
+        if constexpr (WS) mbar_wait(bar(B_W2FULL + b), k & 1);
         T(3);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bd = umma_desc_sw128(sW2 + cv * COUT * 128);
+          const uint64_t bd = umma_desc_sw128(WS ? sW2 + b * C::kW2Chunk : sW2 + cv * COUT * 128);
 #pragma unroll
           for (int t = 0; t < A2T; ++t) {
             const uint64_t ad = umma_desc_sw128(sA2 + b * C::kA2Buf + t * kTile);
@@ -193,18 +232,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
             for (int ks = 0; ks < 4; ++ks) umma_bf16(tD2 + t * COUT, ad + 2 * ks, bd + 2 * ks, idesc2, (cv | ks) != 0);
           }
           umma_commit(bar(B_A2FREE + b));
+          if constexpr (WS) umma_commit(bar(B_W2FREE + b));
           if (cv == NC - 1) umma_commit(bar(B_D2FULL));
         }
         __syncwarp();
         T(4);
       };
       int u = 0;
+      if constexpr (WS) load_w1(0);
       for (int pi = 0; pi < n_mine; ++pi) {
         const int ab = pi % A1BUFS, ak = pi / A1BUFS;
         mbar_wait(bar(B_A1FULL + ab), ak & 1);
         T(0);
         for (int c = 0; c < NC; ++c, ++u) {
           const int b = u & 1, k = u >> 1;
+          if constexpr (WS) {
+            if (u + 1 < n_mine * NC) load_w1(u + 1);   // one unit ahead (its slot was read by the first GEMM of unit u - 1)
+            mbar_wait(bar(B_W1FULL + b), k & 1);
+          }
           mbar_wait(bar(B_D1FREE + b), (k & 1) ^ 1);
           T(1);
           tc_fence_after();
@@ -214,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
 #pragma unroll
               for (int kb = 0; kb < KB1; ++kb) {
                 const uint64_t ad = umma_desc_sw128(sA1 + ab * C::kA1Buf + (kb * TILES + t) * kTile);
-                const uint64_t bd = umma_desc_sw128(sW1 + (kb * CH + c * 64) * 128);
+                const uint64_t bd = umma_desc_sw128(WS ? sW1 + b * C::kW1Chunk + kb * 64 * 128 : sW1 + (kb * CH + c * 64) * 128);
                 constexpr int KS_ALL = (CIN + 15) / 16;
                 const int ks_n = (KS_ALL - kb * 4) < 4 ? (KS_ALL - kb * 4) : 4;
 #pragma unroll
@@ -223,10 +268,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
               }
             }
             umma_commit(bar(B_D1FULL + b));
+            if constexpr (WS) umma_commit(bar(B_W1FREE + b));
             if (c == NC - 1) umma_commit(bar(B_A1FREE + ab));
           }
           __syncwarp();
           T(2);
+          // W2 of this unit: needed by gemm2(u), one step from now; its slot was read by gemm2(u - 2), issued a whole
+          // step ago (asking for it before issue1 made the issuer wait for that MMA group to retire)
+          if constexpr (WS) load_w2(u);
           if (u > 0) gemm2(u - 1);
         }
       }
@@ -464,6 +513,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
     __nv_bfloat162 wt[9][2], wbias[2];
     auto load_taps = [&](int c) {
       const int ch = c * 64 + 4 * g;
+      if constexpr (WS) {   // packed bf16 [CH/8][10][8]: this thread's 4 channels are one half of a 16-byte entry
+        const uint32_t tp = sWD + (uint32_t)(ch >> 3) * 160u + (uint32_t)(g & 1) * 8u;
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const uint2 w2 = lds64(tp + t9 * 16);
+          wt[t9][0] = *reinterpret_cast<const __nv_bfloat162*>(&w2.x);
+          wt[t9][1] = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
+        }
+        const uint2 b2 = lds64(tp + 9 * 16);
+        wbias[0] = *reinterpret_cast<const __nv_bfloat162*>(&b2.x);
+        wbias[1] = *reinterpret_cast<const __nv_bfloat162*>(&b2.y);
+      } else {
 #pragma unroll
       for (int t9 = 0; t9 < 9; ++t9) {
         const float4 w4 = lds_f4(sWD + (t9 * CH + ch) * 4);
@@ -473,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
       const float4 b4 = lds_f4(sBD + ch * 4);
       wbias[0] = __floats2bfloat162_rn(b4.x, b4.y);
       wbias[1] = __floats2bfloat162_rn(b4.z, b4.w);
+      }
     };
     auto tap = [&](__nv_bfloat162* a, const uint2& v, const __nv_bfloat162* w) {
       a[0] = __hfma2(w[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x), a[0]);
@@ -582,11 +644,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
   if (warp == kIssuerWarp) tmem_dealloc(tmem, 512);
 }
 
-template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS>
+template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS, bool WS = false>
 int launch_t(const FusedArgs& a, cudaStream_t st) {
-  using C = FCfg<CIN, COUT, STRIDE, TILES, A1BUFS>;
+  using C = FCfg<CIN, COUT, STRIDE, TILES, A1BUFS, WS>;
   static bool attr_set = false;
-  auto kfn = fused_ir_kernel<CIN, COUT, STRIDE, UPCAT, RES, TILES, A1BUFS>;
+  auto kfn = fused_ir_kernel<CIN, COUT, STRIDE, UPCAT, RES, TILES, A1BUFS, WS>;
+  if (WS && !a.wdp) return (int)cudaErrorInvalidValue;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return (int)e;
@@ -622,6 +685,14 @@ int launch_fused_ir(const FusedArgs& a, cudaStream_t st) {
   CASE(64, 128, 1, false, false, 2, 1)   // audio conv2
   CASE(128, 32, 1, true, false, 1, 2)    // up3.0
 #undef CASE
+#define CASE_WS(CIN_, COUT_, S_, U_, R_, TILES_, A1B_)                                        \
+  if (a.cin == CIN_ && a.cout == COUT_ && a.stride == S_ && a.upcat == U_ && a.res == R_) {   \
+    if (a.batch <= 0) return 0;                                                               \
+    return launch_t<CIN_, COUT_, S_, U_, R_, TILES_, A1B_, true>(a, st);                      \
+  }
+  CASE_WS(128, 128, 1, false, true, 1, 2)   // down2.1 (40x40): weights streamed
+  CASE_WS(256, 64, 1, true, false, 1, 1)    // up2.0   (40x40): weights streamed
+#undef CASE_WS
   return -1;
 }
 

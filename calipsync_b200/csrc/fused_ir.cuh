@@ -12,6 +12,7 @@ struct FusedArgs {
   const uint8_t* W1;         // packed [k-block][2cin rows][128 B]
   const uint8_t* W2;         // packed [k-block][cout rows][128 B]
   const float *wd, *b1, *bd, *b2;
+  const uint8_t* wdp;        // weight-streaming instantiations: depthwise taps + bias as bf16 [2cin/8][10][8]
   int W, batch, num_sms;
   int cin, cout, stride;
   bool upcat, res;

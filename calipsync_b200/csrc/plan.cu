@@ -212,11 +212,11 @@ struct casync_plan {
   bool overlap_cap = true;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // Two-lane split (measured +6 % at batch 64, +4 % at 256, a loss below ~48): the batch is cut into two halves that run
+  // Two-lane split (measured +6 % at batch 64, +4 % at 24 and at 256, a loss at 16): the batch is cut into two halves that run
   // the whole forward on two streams.  The low-resolution kernels are 100-450 CTAs of mostly fixed cost per launch, so
   // the halves' kernels share the GPU instead of leaving SMs idle.  Lane 0 = the caller's stream; lane 1 = `lane1`,
   // forked / joined with events, with its own side stream for the small-batch audio overlap.
-  int split_min_batch = 48;         // CASYNC_SPLIT=0 disables, CASYNC_SPLIT=<n> sets the threshold
+  int split_min_batch = 24;         // CASYNC_SPLIT=0 disables, CASYNC_SPLIT=<n> sets the threshold
   cudaStream_t lane1 = nullptr, side1 = nullptr;
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_lane_go = nullptr, ev_lane_done = nullptr;
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
@@ -403,6 +403,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     f.b1 = p->w<float>(pre + "b1");
     f.bd = p->w<float>(pre + "bd");
     f.b2 = p->w<float>(pre + "b2");
+    f.wdp = p->w<uint8_t>(pre + "wdp");
     f.W = H;
     f.batch = batch;
     f.num_sms = g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms;

@@ -200,6 +200,7 @@ def test_layer_program_launches_are_bit_exact(batch, monkeypatch):
     """CASYNC_CHAIN=1 runs the low-resolution GEMM / depthwise layers as layer programs (chain.cu: one persistent launch,
     tile-granular dependency counters instead of kernel boundaries).  Same arithmetic in the same order: every stage
     tensor and the output must equal the per-layer-launch path bit for bit (ragged row tiles included)."""
+    monkeypatch.setenv("CASYNC_SPLIT", "0")      # stage views describe the unsplit workspace layout
     x, a = O.make_inputs(batch, 5)
     model, _ = make_model("R1", seed=2)
     ref = model(x.cuda(), a.cuda())

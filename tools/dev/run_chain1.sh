@@ -1,8 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for B in 48 64 96 128 256 1024; do
-CASYNC_SPLIT=0 timeout 60 build/casync_run $B 20 0 2>&1 | tail -2 | head -1
-timeout 60 build/casync_run $B 20 0 2>&1 | tail -2 | head -1
-done
-CASYNC_SPLIT=0 timeout 60 build/casync_run 64 4 0 2>&1 | tail -1
-timeout 60 build/casync_run 64 4 0 2>&1 | tail -1
+for i in 4 20; do CASYNC_SPLIT=0 CASYNC_PHASE_DBG=$i timeout 60 build/casync_run 64 10 0 2>&1 | grep -A3 "phase dbg"; done
+CASYNC_SPLIT=0 timeout 60 build/casync_run 64 20 1 2>&1 | grep -E "batch|down2.1|up2.0|total"
+timeout 60 build/casync_run 64 30 0 2>&1 | tail -2 
