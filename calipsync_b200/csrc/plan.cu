@@ -234,7 +234,7 @@ struct casync_plan {
   mutable long launches_chunk = 0;  // kernels the last forward launched per chunk (measured)
   mutable Chain chain;
   mutable std::vector<ChainSlot> slots;
-  mutable int seg = 0;
+  mutable int seg = 0, seg_base = 0;
   mutable unsigned char* arena = nullptr;   // hidden tensors of the InvertedResidual blocks inside one program: every
   mutable size_t arena_cap = 0, arena_off = 0;   // buffer is written once per launch (no WAR hazards between items)
   template <class T>
@@ -376,7 +376,7 @@ bf16* arena_alloc(const casync_plan* p, size_t elems) {
 }
 void chain_begin(const casync_plan* p, const Workspace& w, int frames) {
   p->chain.reset();
-  p->seg = 0;
+  p->seg = p->seg_base;   // each lane of a split batch has its own descriptor slots
   p->arena = reinterpret_cast<unsigned char*>(w["h1"]);
   p->arena_cap = (w.offs[w.index("h2")] - w.offs[w.index("h1")]) + align256((size_t)25600 * 128 * 2 * frames);
   p->arena_off = 0;
@@ -893,6 +893,7 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
     const float* xc = x + (size_t)f0 * 6 * 25600;
     const float* ac = audio + (size_t)f0 * 32768;
     uint8_t* oc = reinterpret_cast<uint8_t*>(out) + (size_t)f0 * out_frame;
+    // (layer programs are persistent 148-CTA launches that cannot share the GPU: measured 3.21 ms with both, 2.70 ms alone)
     if (nb >= plan->split_min_batch && !plan->use_chain && !g_prof && plan->lane1) {
       // two lanes: frames [0, h0) on the caller's stream, [h0, nb) on the plan's second stream, joined at the end
       const int hcap = (cap + 1) / 2, h0 = (nb + 1) / 2, h1 = nb - h0;
@@ -900,9 +901,12 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
       Workspace w1(reinterpret_cast<uint8_t*>(workspace) + w0.total, hcap);
       CK(cudaEventRecord(plan->ev_lane_go, st));
       CK(cudaStreamWaitEvent(plan->lane1, plan->ev_lane_go, 0));
+      plan->seg_base = 0;
       int e = forward_chunk(plan, xc, ac, oc, w0, h0, flags, st, 0);
+      plan->seg_base = 64;
       if (!e) e = forward_chunk(plan, xc + (size_t)h0 * 6 * 25600, ac + (size_t)h0 * 32768, oc + (size_t)h0 * out_frame, w1, h1,
                                 flags, plan->lane1, 1);
+      plan->seg_base = 0;
       CK(cudaEventRecord(plan->ev_lane_done, plan->lane1));
       CK(cudaStreamWaitEvent(st, plan->ev_lane_done, 0));
       if (e) return e;
