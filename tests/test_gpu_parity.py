@@ -214,3 +214,23 @@ def test_layer_program_launches_are_bit_exact(batch, monkeypatch):
     assert torch.equal(out, ref)
     out2 = chained(x.cuda(), a.cuda())           # second call: cached descriptors, re-zeroed counters
     assert torch.equal(out2, ref)
+
+
+@pytest.mark.parametrize("batch", [25, 70])
+def test_two_lane_split_is_bit_exact(batch, monkeypatch):
+    """Batches >= 24 run as two half-batches on two streams.  Frames are independent, so the result must
+    equal the single-stream forward bit for bit -- odd batch sizes (unequal halves) included -- and the caller's stream
+    must see the joined result without an explicit synchronisation."""
+    x, a = O.make_inputs(batch, 9)
+    xs, as_ = x.cuda(), a.cuda()
+    split, _ = make_model("R1", seed=3)
+    out = split(xs, as_)
+    doubled = out * 2.0                            # consumer on the caller's stream, enqueued right behind the forward
+    assert split.launches_per_forward(batch) == 2 * split.launches_per_forward(8)
+    monkeypatch.setenv("CASYNC_SPLIT", "0")
+    single, _ = make_model("R1", seed=3)
+    ref = single(xs, as_)
+    assert single.launches_per_forward(batch) == single.launches_per_forward(8)
+    assert torch.equal(out, ref)
+    assert torch.equal(doubled, ref * 2.0)
+    assert torch.equal(split.forward_uint8(xs, as_), single.forward_uint8(xs, as_))
