@@ -24,6 +24,7 @@ SYMBOLS = [
     ("casync_prepare_inputs", _I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     ("casync_stage_view", _I, [_P, _I, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     ("casync_launches_per_forward", _I64, [_P, _I]),
+    ("casync_graph_replays", _I64, [_P]),
     ("casync_ir_count", _I, []),
     ("casync_ir_info", _I, [_I, C.POINTER(C.c_char_p)] + [C.POINTER(_I)] * 5),
     ("casync_stage_scratch_bytes", _SZ, [_P, _I]),

@@ -235,6 +235,31 @@ struct casync_plan {
   mutable Chain chain;
   mutable std::vector<ChainSlot> slots;
   mutable int seg = 0, seg_base = 0;
+  // CUDA graphs: a forward is 70-140 launches plus fork / join events; below batch ~16 the host cannot enqueue them as
+  // fast as the GPU retires them (batch 8: 0.39 ms of enqueue per 0.62 ms step).  The launch sequence only depends on
+  // (x, audio, out, workspace, batch, flags), so the second call with the same key is captured from the caller's stream
+  // (lanes and side streams join the capture through their events), instantiated and kept (LRU, 16 entries); every
+  // later call is one cudaGraphLaunch.  CASYNC_GRAPH=0 disables.  Any failure falls back to eager launches for good.
+  struct GraphKey {
+    const void *x, *audio, *out, *ws;
+    int batch;
+    unsigned flags;
+    bool operator==(const GraphKey& o) const {
+      return x == o.x && audio == o.audio && out == o.out && ws == o.ws && batch == o.batch && flags == o.flags;
+    }
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    unsigned long long last_use;
+  };
+  cudaStream_t cap_stream = nullptr;   // capture origin (the caller's stream may be the legacy default stream, which
+                                       // cannot be captured); the instantiated graph is launched into the caller's
+  mutable bool use_graphs = true;
+  mutable std::vector<GraphEntry> graphs;
+  mutable std::vector<GraphKey> seen;
+  mutable unsigned long long graph_tick = 0;
+  mutable long graph_replays = 0, graph_captures = 0;
   mutable unsigned char* arena = nullptr;   // hidden tensors of the InvertedResidual blocks inside one program: every
   mutable size_t arena_cap = 0, arena_off = 0;   // buffer is written once per launch (no WAR hazards between items)
   template <class T>
@@ -778,8 +803,10 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
       return fail(CASYNC_ECUDA, "cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
+  if (const char* c = getenv("CASYNC_GRAPH")) p->use_graphs = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_SPLIT")) p->split_min_batch = atoi(c) > 0 ? atoi(c) : (1 << 30);
-  if (cudaStreamCreateWithFlags(&p->lane1, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&p->lane1, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&p->side1, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_fork1, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_join1, cudaEventDisableTiming) != cudaSuccess ||
@@ -830,6 +857,10 @@ void casync_plan_destroy(casync_plan* plan) {
   }
   if (plan) chain_dbg_report();
   if (plan) {
+    for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    plan->graphs.clear();
+  }
+  if (plan) {
     for (auto& sl : plan->slots)
       if (sl.dev) cudaFree(sl.dev);
     if (plan->side) {
@@ -838,7 +869,7 @@ void casync_plan_destroy(casync_plan* plan) {
     }
     if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
     if (plan->ev_join) cudaEventDestroy(plan->ev_join);
-    for (cudaStream_t st : {plan->lane1, plan->side1})
+    for (cudaStream_t st : {plan->lane1, plan->side1, plan->cap_stream})
       if (st) {
         cudaStreamSynchronize(st);
         cudaStreamDestroy(st);
@@ -850,6 +881,7 @@ void casync_plan_destroy(casync_plan* plan) {
 }
 
 int casync_chunk_frames(const casync_plan* plan) { return plan ? plan->chunk : 0; }
+int64_t casync_graph_replays(const casync_plan* plan) { return plan ? plan->graph_replays : 0; }
 
 size_t casync_workspace_bytes(const casync_plan* plan, int batch) {
   if (!plan || batch <= 0) return 0;
@@ -879,13 +911,8 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
   return total;
 }
 
-int casync_forward(const casync_plan* plan, const float* x, const float* audio, void* out, void* workspace, int batch,
-                   unsigned flags, void* stream) {
-  if (!plan || !x || !audio || !out || !workspace) return fail(CASYNC_EINVAL, "null argument");
-  if (batch <= 0) return fail(CASYNC_EINVAL, "batch must be positive, got %d", batch);
-  if (flags & CASYNC_F_FP32) return fail(CASYNC_EUNSUP, "fp32 arithmetic path is not implemented");
-  if ((uintptr_t)workspace & 255) return fail(CASYNC_EINVAL, "workspace must be 256-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+static int forward_eager(const casync_plan* plan, const float* x, const float* audio, void* out, void* workspace,
+                         int batch, unsigned flags, cudaStream_t st) {
   const size_t out_frame = (flags & CASYNC_F_OUT_U8_HWC) ? 76800 : 76800 * 4;
   const int cap = batch < plan->chunk ? batch : plan->chunk;
   for (int f0 = 0; f0 < batch; f0 += plan->chunk) {
@@ -916,6 +943,74 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
     int e = forward_chunk(plan, xc, ac, oc, w, nb, flags, st);
     if (e) return e;
   }
+  return 0;
+}
+
+int casync_forward(const casync_plan* plan, const float* x, const float* audio, void* out, void* workspace, int batch,
+                   unsigned flags, void* stream) {
+  if (!plan || !x || !audio || !out || !workspace) return fail(CASYNC_EINVAL, "null argument");
+  if (batch <= 0) return fail(CASYNC_EINVAL, "batch must be positive, got %d", batch);
+  if (flags & CASYNC_F_FP32) return fail(CASYNC_EUNSUP, "fp32 arithmetic path is not implemented");
+  if ((uintptr_t)workspace & 255) return fail(CASYNC_EINVAL, "workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!plan->use_graphs || plan->use_chain || g_prof) return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();   // the caller is capturing this stream itself: our launches simply join its graph
+    return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  }
+  const casync_plan::GraphKey key{x, audio, out, workspace, batch, flags};
+  ++plan->graph_tick;
+  for (auto& g : plan->graphs)
+    if (g.key == key) {
+      g.last_use = plan->graph_tick;
+      cudaError_t le = cudaGraphLaunch(g.exec, st);
+      if (le != cudaSuccess) return fail(CASYNC_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(le));
+      ++plan->graph_replays;
+      return 0;
+    }
+  bool seen = false;
+  for (const auto& k : plan->seen) seen = seen || k == key;
+  if (!seen) {   // first occurrence: plain launches (also performs the one-time function-attribute calls)
+    if (plan->seen.size() >= 64) plan->seen.erase(plan->seen.begin());
+    plan->seen.push_back(key);
+    return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  }
+  // a caller whose tensors never settle on a few addresses would pay for a capture per call: stop after a while
+  if (plan->graph_captures >= 48 && plan->graph_replays < 4 * plan->graph_captures) {
+    plan->use_graphs = false;
+    return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  }
+  ++plan->graph_captures;
+  // second occurrence: capture (on the plan's own stream) and instantiate
+  if (!plan->cap_stream || cudaStreamBeginCapture(plan->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    plan->use_graphs = false;
+    return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  }
+  const int e = forward_eager(plan, x, audio, out, workspace, batch, flags, plan->cap_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(plan->cap_stream, &graph);
+  cudaGraphExec_t exec = nullptr;
+  if (!e && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e || ce != cudaSuccess || !exec) {   // nothing ran: give up on graphs for this plan and run the call eagerly
+    cudaGetLastError();
+    plan->use_graphs = false;
+    if (exec) cudaGraphExecDestroy(exec);
+    return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  }
+  if (plan->graphs.size() >= 16) {
+    size_t lru = 0;
+    for (size_t i = 1; i < plan->graphs.size(); ++i)
+      if (plan->graphs[i].last_use < plan->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(plan->graphs[lru].exec);
+    plan->graphs.erase(plan->graphs.begin() + lru);
+  }
+  plan->graphs.push_back({key, exec, plan->graph_tick});
+  cudaError_t le = cudaGraphLaunch(exec, st);
+  if (le != cudaSuccess) return fail(CASYNC_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(le));
+  ++plan->graph_replays;
   return 0;
 }
 

@@ -268,3 +268,7 @@ class Model(nn.Module):
 
     def launches_per_forward(self, batch):
         return int(_lib.load().casync_launches_per_forward(self._plan[0], batch)) if self._plan else 0
+
+    def graph_replays(self):
+        """Forwards replayed from a cached CUDA graph so far (same tensors / batch seen before; CASYNC_GRAPH=0 disables)."""
+        return int(_lib.load().casync_graph_replays(self._plan[0])) if self._plan else 0

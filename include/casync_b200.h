@@ -100,6 +100,9 @@ CASYNC_API int casync_forward_profiled(const casync_plan *plan, const float *x_n
 CASYNC_API int casync_stage_view(const casync_plan *plan, int batch, const char *name, size_t *offset, int64_t *rows,
                       int64_t *cols, int64_t *ld);
 CASYNC_API int64_t casync_launches_per_forward(const casync_plan *plan, int batch);
+/* Forwards of this plan that were replayed from a cached CUDA graph (the second call with the same pointers, batch
+ * and flags is captured; CASYNC_GRAPH=0 disables). */
+CASYNC_API int64_t casync_graph_replays(const casync_plan *plan);
 
 /* Per-stage entry points (unit tests / ncu).  Activations are NHWC bf16, `scratch` is device memory of
  * at least casync_stage_scratch_bytes(plan, batch).

@@ -234,3 +234,31 @@ def test_two_lane_split_is_bit_exact(batch, monkeypatch):
     assert torch.equal(out, ref)
     assert torch.equal(doubled, ref * 2.0)
     assert torch.equal(split.forward_uint8(xs, as_), single.forward_uint8(xs, as_))
+
+
+@pytest.mark.parametrize("batch", [3, 40])
+def test_cuda_graph_replay_matches_eager(batch, monkeypatch):
+    """The second forward with the same tensors is captured into a CUDA graph and later calls replay it (one
+    cudaGraphLaunch instead of 70-140 launches + fork / join events).  Replays must see NEW input values in the same
+    buffers and give exactly the eager result; other tensors keep working next to the cached graph."""
+    model, _ = make_model("R1", seed=4)
+    x, a = O.make_inputs(batch, 21)
+    xs, as_ = x.cuda(), a.cuda()
+    out = torch.empty(batch, 3, 160, 160, device="cuda")
+    run = lambda: model._run(xs, as_, out, 0).clone()   # noqa: E731  (fixed output buffer -> a stable key; flags 0 = bf16 path)
+    first = run()                       # eager
+    second = run()                      # captured + launched
+    third = run()                       # replayed
+    assert model.graph_replays() >= 2
+    assert torch.equal(first, second) and torch.equal(first, third)
+    x2, a2 = O.make_inputs(batch, 22)
+    xs.copy_(x2.cuda())
+    as_.copy_(a2.cuda())
+    replayed = run()                    # same buffers, new contents
+    monkeypatch.setenv("CASYNC_GRAPH", "0")
+    eager_model, _ = make_model("R1", seed=4)
+    ref = eager_model(xs, as_)
+    assert eager_model.graph_replays() == 0
+    assert torch.equal(replayed, ref)
+    assert not torch.equal(replayed, first)
+    assert torch.equal(model(xs, as_), ref)   # fresh output tensor: different key, still correct

@@ -112,7 +112,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&out, (size_t)B * 76800 * 4));
   cudaStream_t st;
   CK(cudaStreamCreate(&st));
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3 * nsets; ++i)   // every input set three times: eager, graph capture, first replay
     if (casync_forward(plan, xs[i % nsets], as[i % nsets], out, ws, B, flags, st)) {
       fprintf(stderr, "forward: %s\n", casync_last_error());
       return 1;

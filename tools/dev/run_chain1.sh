@@ -1,9 +1,6 @@
 cd $GRAFT_REPO_ROOT
-for B in 24 64 256; do
-timeout 60 build/casync_run $B 20 0 2>&1 | tail -2
-CASYNC_CHAIN=1 timeout 60 build/casync_run $B 20 0 2>&1 | tail -2
-done
-for B in 1 8; do
-timeout 60 build/casync_run $B 50 0 2>&1 | tail -2 | head -1
-CASYNC_CHAIN=1 timeout 60 build/casync_run $B 50 0 2>&1 | tail -2 | head -1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for B in 1 2 4 8 16 32 64 256; do
+CASYNC_GRAPH=0 timeout 60 build/casync_run $B 60 0 2>&1 | tail -2 | head -1
+timeout 60 build/casync_run $B 60 0 2>&1 | tail -2 | head -1
 done
