@@ -231,7 +231,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, period=1):
+        # untimed prelude before the W warm-up steps: the library captures a CUDA graph the second time it sees the same
+        # tensors, so every buffer set is visited twice (eager, capture) before anything counts -- the steady state a
+        # caller with a fixed set of buffers is in
+        for i in range(2 * period):
+            fn(i)
         for i in range(warmup):
             fn(i)
         barrier()
@@ -254,7 +259,7 @@ def main():
         net(x, a)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, t0, t1 = timed(step_dev, args.steps, max(3, args.warmup))
+    ms, t0, t1 = timed(step_dev, args.steps, max(3, args.warmup), nsets)
     clocks = sampler.stop(t0, t1) if sampler else None
     fps = world * B * args.steps / (ms / 1e3)
 
@@ -272,11 +277,11 @@ def main():
         out = net(hx.to(device, non_blocking=True), ha.to(device, non_blocking=True))
         host_out[i % 2].copy_(out, non_blocking=True)
 
-    ms_seq, _, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    ms_seq, _, _ = timed(step_e2e, args.steps, max(3, args.warmup), 2)
     fps_e2e_seq = world * B * args.steps / (ms_seq / 1e3)
 
     def timed_pipeline(pipe, outs, steps, warmup):
-        for i in range(warmup):
+        for i in range(warmup + 8):                 # + graph priming: every device slot seen twice (see timed())
             pipe.submit(*host_sets[i % 2], outs[i % 2])
         pipe.flush()
         barrier()
@@ -352,8 +357,8 @@ def main():
         for b in (1, 8, 256, 1024):
             try:
                 xs = [synth_inputs(b, device, 7 + i) for i in range(2 if b >= 256 else 8)]
-                n = max(3, min(20, 4096 // b))
-                m, _, _ = timed(lambda i: net(*xs[i % len(xs)]), n, 3)
+                n = max(3, min(40, 4096 // b))
+                m, _, _ = timed(lambda i: net(*xs[i % len(xs)]), n, 3, len(xs))
                 sweep[str(b)] = round(b * n / (m / 1e3), 1)
                 del xs
             except Exception as e:      # report, never hide

@@ -238,8 +238,8 @@ struct casync_plan {
   // CUDA graphs: a forward is 70-140 launches plus fork / join events; below batch ~16 the host cannot enqueue them as
   // fast as the GPU retires them (batch 8: 0.39 ms of enqueue per 0.62 ms step).  The launch sequence only depends on
   // (x, audio, out, workspace, batch, flags), so the second call with the same key is captured from the caller's stream
-  // (lanes and side streams join the capture through their events), instantiated and kept (LRU, 16 entries); every
-  // later call is one cudaGraphLaunch.  CASYNC_GRAPH=0 disables.  Any failure falls back to eager launches for good.
+  // (lanes and side streams join the capture through their events), instantiated and kept (LRU, 16 entries; a key must
+  // recur within 8 calls to be captured); every later call is one cudaGraphLaunch.  CASYNC_GRAPH=0 disables.  Any failure falls back to eager launches for good.
   struct GraphKey {
     const void *x, *audio, *out, *ws;
     int batch;
@@ -971,8 +971,10 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
     }
   bool seen = false;
   for (const auto& k : plan->seen) seen = seen || k == key;
-  if (!seen) {   // first occurrence: plain launches (also performs the one-time function-attribute calls)
-    if (plan->seen.size() >= 64) plan->seen.erase(plan->seen.begin());
+  if (!seen) {   // not among the last 8 calls: plain launches (also performs the one-time function-attribute calls).
+    // A key is only captured when it recurs within 8 calls, and 16 graphs are kept: callers that rotate through many
+    // buffers (bench.py's L2-defeating input sets at small batch) stay eager instead of capturing on every call.
+    if (plan->seen.size() >= 8) plan->seen.erase(plan->seen.begin());
     plan->seen.push_back(key);
     return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
   }
