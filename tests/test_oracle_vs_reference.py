@@ -74,3 +74,47 @@ def test_input_assembly_equals_reference_code():
         want.append(np.concatenate([img_real_ex, img_masked]))
     got = O.assemble_x(crops168[:, 4:164, 4:164])
     assert torch.equal(got, torch.from_numpy(np.stack(want)))
+
+
+def test_hubert_extraction_restatement_equals_reference():
+    """BASELINE config 4's upstream stage: tools/e2e_hubert.extract_features restates HubertExtractor.extract_features
+    (utils/hubert_extractor.py:18-58: 1000-step clips, pad / trim to expected_T, drop an odd frame, [-1, 2, 1024]).
+    Checked live against the reference method on a small random HuBERT (the pretrained weights are not on disk)."""
+    import importlib.util
+    import sys
+    import types
+    from conftest import REFERENCE_DIR, ROOT, have_reference
+    if not have_reference():
+        pytest.skip("reference checkout not present on this machine")
+    transformers = pytest.importorskip("transformers")
+    fe_cls, hubert_cls, cfg_cls = transformers.Wav2Vec2FeatureExtractor, transformers.HubertModel, transformers.HubertConfig
+    _ = transformers.Wav2Vec2Processor                                          # resolve the lazy imports first
+    if "soundfile" not in sys.modules:                                          # imported at the reference module's top,
+        import importlib.machinery                                              # never used here
+        stub = types.ModuleType("soundfile")
+        stub.__spec__ = importlib.machinery.ModuleSpec("soundfile", None)
+        sys.modules["soundfile"] = stub
+    spec = importlib.util.spec_from_file_location("ref_hubert_extractor", REFERENCE_DIR + "/utils/hubert_extractor.py")
+    ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_mod)
+    sys.modules.setdefault("bench", types.ModuleType("bench"))                  # e2e_hubert only needs bench in main()
+    spec2 = importlib.util.spec_from_file_location("e2e_hubert", ROOT + "/tools/e2e_hubert.py")
+    ours = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(ours)
+
+    cfg = cfg_cls(hidden_size=1024, num_hidden_layers=1, num_attention_heads=16, intermediate_size=64,
+                                    feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True)
+    torch.manual_seed(0)
+    model = hubert_cls(cfg).eval()
+    ext = object.__new__(ref_mod.HubertExtractor)       # no checkpoint to load: wire the members by hand
+    ext.device = "cpu"
+    ext.model = model
+    ext.processor = fe_cls(feature_size=1, sampling_rate=16000, padding_value=0.0,
+                                                          do_normalize=True, return_attention_mask=False)
+    for seconds in (3.0, 20.5, 41.03):                   # below one clip, one clip + remainder, two clips + short tail
+        speech = (torch.randn(int(seconds * 16000), generator=torch.Generator().manual_seed(int(seconds))) * 0.1)
+        want = ext.extract_features(speech.numpy())
+        got = ours.extract_features(model, speech)
+        assert tuple(got.shape) == tuple(want.shape)
+        assert float((got - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
+    ext.model = ext.processor = None

@@ -46,3 +46,18 @@ def test_folded_weights_reproduce_oracle(regime):
     with torch.no_grad():
         out, _ = PackedNet(sd, round_bf16=True).forward(x, a)      # + bf16 activations between kernels
     assert O.max_abs_255(out, ref) < 2.0 and O.psnr_db(out, ref) > 45.0
+
+
+def test_packed_depthwise_taps_layout():
+    """`wdp` = depthwise taps + folded-BN bias as bf16, [hid/8][10][8]: entry (chunk, t, e) is tap t (t = 9: the bias)
+    of channel 8*chunk + e, rounded fp64 -> fp32 -> bf16 exactly like the fp32 taps the fused kernel converts on the
+    device -- the stand-alone depthwise kernel, the weight-streaming fused blocks and the layer programs read it."""
+    sd = O.make_state_dict(0, "R1")
+    entries = packer.build_entries(sd)
+    for prefix, hid in (("down4.maxpool_conv.0.double_conv.1", 1024), ("audio_model.conv4", 512)):
+        wdp = torch.from_numpy(entries[prefix + "|wdp"]).view(torch.bfloat16).view(hid // 8, 10, 8).float()
+        wd = torch.from_numpy(entries[prefix + "|wd"]).view(torch.float32).view(9, hid)
+        bd = torch.from_numpy(entries[prefix + "|bd"]).view(torch.float32)
+        for t in range(9):
+            assert torch.equal(wdp[:, t, :].reshape(-1), wd[t].bfloat16().float()), (prefix, t)
+        assert torch.equal(wdp[:, 9, :].reshape(-1), bd.bfloat16().float()), prefix

@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for B in 1 2 4 8 16 32 64 256; do
-CASYNC_GRAPH=0 timeout 60 build/casync_run $B 60 0 2>&1 | tail -2 | head -1
-timeout 60 build/casync_run $B 60 0 2>&1 | tail -2 | head -1
+for l in down4.1.pw2 fuse0.0.pw1 "attention_blocks.0|b1_w"; do
+CASYNC_GRAPH=0 CASYNC_SPLIT=0 CASYNC_GEMM_DBG="$l" timeout 60 build/casync_run 64 10 0 2>&1 | grep -A2 "gemm dbg"
 done
