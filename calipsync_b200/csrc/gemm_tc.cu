@@ -35,22 +35,29 @@ constexpr int kEpiWarps = 8;          // dedicated epilogue warps (the 8 produce
 constexpr int kThreads = kProducers + 2 * 32 + kEpiWarps * 32;
 constexpr int kLag = 2;              // A stages in flight per producer thread before publishing
 
-template <int BN>
+// DWE ("depthwise in the epilogue", BN = 256 only): the GEMM is the first 1x1 conv of an InvertedResidual on a W x W
+// image with W*W <= 128 (the 10x10 stages).  Row tiles are FRAME-aligned (tile = the W*W pixels of one frame, the other
+// accumulator rows are ignored), so the epilogue holds a frame's hidden tile [W*W, 256 channels]: it goes to shared
+// memory as bf16 and the same 8 warps apply the depthwise 3x3 (+ folded-BN bias + LeakyReLU) from there and store the
+// block's SECOND hidden tensor -- no depthwise launch, no round trip of the first one (module/unet.py:17-27).
+constexpr int kHidTileRows = 100;
+template <int BN, bool DWE = false>
 struct Cfg {
   static constexpr int kStage = kABytes + BN * 128;
+  static constexpr int kHidTile = DWE ? kHidTileRows * BN * 2 : 0;
   static constexpr int kExtra = 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue vectors*/ +
                                 16384 /*epilogue store staging: 8 warps x 32 rows x 64 B*/;
-  static constexpr int S = (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;   // 256:4  128:6  64:8  32:8
-  static constexpr int kSmem = S * kStage + kExtra;
+  static constexpr int S = DWE ? 3 : (200 * 1024) / kStage > 8 ? 8 : (200 * 1024) / kStage;   // 256:4  128:6  64:8  32:8
+  static constexpr int kSmem = S * kStage + kExtra + kHidTile;
   static_assert(kSmem <= 232448, "shared memory overflow");
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
   static constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
                                    : 2 * kAccCols <= 256 ? 256 : 512;   // tcgen05.alloc wants a power of two
 };
 
-template <int BN>
+template <int BN, bool DWE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, DWE>;
   constexpr int S = C::S;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,7 +82,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
     }
   };
   const int KB = (p.K + 63) >> 6;
-  const int NT = p.N / BN, MT = (p.M + kBM - 1) / kBM;
+  const int tile_rows = DWE ? p.dw_w * p.dw_w : kBM;   // DWE: one frame per row tile
+  const int NT = p.N / BN, MT = (p.M + tile_rows - 1) / tile_rows;
   const int n_tiles = NT * MT;
   // epilogue column groups (4 warps each, one per TMEM lane quarter).  Letting the idle producer warps of the
   // TMA-loaded mode drain too (16 epilogue warps) was measured SLOWER: a warp's chunk is a serial latency chain
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
-      const int n0 = (tile % NT) * BN, m0 = (tile / NT) * kBM;
+      const int n0 = (tile % NT) * BN, m0 = (tile / NT) * tile_rows;
       float* const ev = evec + (t & 1) * 1024;
       if (et < BN) {
         ev[et] = __ldg(p.bias + n0 + et);
@@ -142,6 +150,85 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
       const int m = m0 + lg * 32 + lane;
       const bool row_ok = m < p.M;
       const int cbeg = cg * cols_per, cend = cbeg + cols_per;
+      if constexpr (DWE) {
+        // ---- pass 1: hidden tile = leaky(acc + b1) as bf16 -> shared memory [pixel][BN channels]; the 16-byte chunks
+        //      of a row are XOR-swizzled with the row index (row pitch 512 B: conflict-free 512-byte warp accesses)
+        const int r = lg * 32 + lane;                  // accumulator row = pixel of this tile's frame
+        const bool px_ok = r < tile_rows && row_ok;
+        uint8_t* const hid = smem_raw + (bar_base + 256 + 8192 + 16384 - smem_u32(smem_raw));
+        // taps + bias of the 8 channels this thread handles in pass 2 (constants: requested before the accumulator wait)
+        const int dc = et & (BN / 8 - 1), dr0 = et / (BN / 8);
+        uint4 wt[9], wb;
+        {
+          const uint4* tp = reinterpret_cast<const uint4*>(p.dwp) + (size_t)((n0 >> 3) + dc) * 10;
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) wt[t9] = __ldg(tp + t9);
+          wb = __ldg(tp + 9);
+        }
+        mbar_wait(acc_full(ab), (t >> 1) & 1);
+        T(8);
+        tc_fence_after();
+        const uint32_t trow = tmem + ab * C::kAccCols + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(trow + c0, acc);
+          tmem_ld_wait32(acc);
+          if (px_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g);
+              const float4 b1 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
+                if (p.leaky) v[q] = fmaxf(v[q], kLeaky * v[q]);
+              }
+              const uint32_t ci = (uint32_t)(c0 >> 3) + g;
+              *reinterpret_cast<uint4*>(hid + r * (BN * 2) + ((ci ^ (uint32_t)(r & 7)) << 4)) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty(ab));                    // the accumulator is free: the next tile's main loop may proceed
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_n) : "memory");   // hidden tile complete
+        T(13);
+        // ---- pass 2: depthwise 3x3 + folded-BN bias + LeakyReLU from the hidden tile (same arithmetic and order as
+        //      dw3x3_kernel: taps outside the image contribute w * 0), 16-byte stores of whole 512-byte row pieces
+        const int Wd = p.dw_w;
+        const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
+#pragma unroll 1
+        for (int px = dr0; px < tile_rows; px += kEpiWarps * 32 / (BN / 8)) {
+          const int y = px / Wd, x = px - y * Wd;
+          __nv_bfloat162 a4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a4[q] = reinterpret_cast<const __nv_bfloat162*>(&wb)[q];
+#pragma unroll
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const int yy = y + t9 / 3 - 1, xx = x + t9 % 3 - 1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (yy >= 0 && yy < Wd && xx >= 0 && xx < Wd) {
+              const int rr = yy * Wd + xx;
+              v = *reinterpret_cast<const uint4*>(hid + rr * (BN * 2) + (((uint32_t)dc ^ (uint32_t)(rr & 7)) << 4));
+            }
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&wt[t9]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a4[q] = __hfma2(pw[q], pv[q], a4[q]);
+          }
+          uint4 o;
+          __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) po[q] = __hmax2(a4[q], __hmul2(a4[q], kslope));
+          if (m0 + px < p.M) *reinterpret_cast<uint4*>(p.C + (size_t)(m0 + px) * p.ldc + n0 + dc * 8) = o;
+        }
+        T(15);
+        // (the bar.sync at the top of the next tile orders these reads before the next pass 1 overwrites the tile)
+        continue;
+      }
       // residual rows (a launch uses res_pre or res_post, never both): the first 32-column chunk is requested BEFORE
       // waiting for the accumulator, so its latency hides behind the tile's main loop; later chunks are prefetched
       // one chunk ahead, behind the TMEM load + arithmetic of the current chunk
@@ -254,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
     if (warp == 0) {
       int j = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / NT) * kBM;
+        const int m0 = (tile / NT) * tile_rows;
         for (int kb = 0; kb < KB; ++kb, ++j) {
           const int s = j % S;
           mbar_wait(empty(s), ((j / S) & 1) ^ 1);
@@ -453,9 +540,10 @@ int gemm_num_sms() { return g_num_sms; }
 
 namespace {
 
-template <int BN>
+template <int BN, bool DWE = false>
 int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
-  const int tiles = (a.N / BN) * ((a.M + kBM - 1) / kBM);
+  const int tile_rows = DWE ? a.dw_w * a.dw_w : kBM;
+  const int tiles = (a.N / BN) * ((a.M + tile_rows - 1) / tile_rows);
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   const int grid = tiles < cap ? tiles : cap;
   alignas(64) CUtensorMap tm;
@@ -465,12 +553,13 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     const int e = gemm_encode_map(&tm, a.A, a.M, a.K, a.lda, kBM, true);
     if (e) return e;
   }
-  return (int)launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, stream, a, tm);
+  return (int)launch_pdl(gemm_tc_kernel<BN, DWE>, dim3(grid), dim3(kThreads), Cfg<BN, DWE>::kSmem, stream, a, tm);
 }
 
-template <int BN>
+template <int BN, bool DWE = false>
 int set_attr() {
-  return (int)cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+  return (int)cudaFuncSetAttribute(gemm_tc_kernel<BN, DWE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg<BN, DWE>::kSmem);
 }
 
 // work-per-SM proxy: waves of tiles x (per-tile cost ~ A bytes + B bytes per k-block, the L2->smem traffic)
@@ -502,12 +591,20 @@ int gemm_init() {
   e |= set_attr<128>();
   e |= set_attr<192>();
   e |= set_attr<256>();
+  e |= set_attr<256, true>();
   return e;
 }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
   if (a.N % 32 != 0 || a.K % 64 != 0) return (int)cudaErrorInvalidValue;   // whole 64-channel k-blocks only
+  if (a.dw_epi) {   // depthwise in the epilogue: frame-aligned tiles, BN = 256 (see Cfg)
+    const int px = a.dw_w * a.dw_w;
+    if (a.amode != A_PLAIN || a.N % 256 != 0 || px < 1 || px > kHidTileRows || a.M % px != 0 || !a.dwp || a.ldc != a.N ||
+        a.res_pre || a.res_post || a.post_scale || a.vt || ((uintptr_t)a.dwp & 15))
+      return (int)cudaErrorInvalidValue;
+    return launch_cfg<256, true>(a, stream);
+  }
   const long mt = (a.M + kBM - 1) / kBM;
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   int best = 32;

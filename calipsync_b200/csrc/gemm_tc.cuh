@@ -33,6 +33,10 @@ struct GemmArgs {
   // can use V^T as a K-major B operand of tcgen05.mma (module/unet.py:215: out = V . attn^T)
   __nv_bfloat16* vt;
   int vt_col0;
+  // first 1x1 conv of an InvertedResidual on a dw_w x dw_w image with dw_w^2 <= 100 pixels: apply the block's depthwise
+  // 3x3 (+ folded-BN bias + LeakyReLU; taps dwp = bf16 [N/8][10][8]) in the epilogue and store ITS output to C [M, N]
+  int dw_epi, dw_w;
+  const uint8_t* dwp;
   unsigned long long* dbg;  // developer timing (CASYNC_GEMM_DBG=<label substring>): per-role cycle counters [16]
 };
 

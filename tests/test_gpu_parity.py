@@ -262,3 +262,23 @@ def test_cuda_graph_replay_matches_eager(batch, monkeypatch):
     assert torch.equal(replayed, ref)
     assert not torch.equal(replayed, first)
     assert torch.equal(model(xs, as_), ref)   # fresh output tensor: different key, still correct
+
+
+@pytest.mark.parametrize("batch", [3, 30])
+def test_depthwise_in_gemm_epilogue_is_bit_exact(batch, monkeypatch):
+    """10x10 InvertedResidual blocks: the depthwise 3x3 runs in the epilogue of the first 1x1 conv (frame-aligned row
+    tiles, hidden tile in shared memory) instead of its own launch.  Same operands, same order of operations: outputs and
+    stage tensors must equal the three-launch path bit for bit."""
+    monkeypatch.setenv("CASYNC_SPLIT", "0")
+    monkeypatch.setenv("CASYNC_DWEPI", "1")      # opt-in (measured neutral at batch 64, DESIGN.md 3.2)
+    x, a = O.make_inputs(batch, 31)
+    fused, _ = make_model("R1", seed=5)
+    out = fused(x.cuda(), a.cuda())
+    stages = {n: fused.stage(n, batch).clone() for n in ("x5", "audio", "kx", "fuse")}
+    monkeypatch.setenv("CASYNC_DWEPI", "0")
+    plain, _ = make_model("R1", seed=5)
+    ref = plain(x.cuda(), a.cuda())
+    assert fused.launches_per_forward(batch) == plain.launches_per_forward(batch) - 7
+    for n, t in stages.items():
+        assert torch.equal(plain.stage(n, batch), t), n
+    assert torch.equal(out, ref)
