@@ -67,7 +67,11 @@ CASYNC_API size_t casync_workspace_bytes(const casync_plan *plan, int batch);
  *   x_nchw   fp32 [batch,6,160,160]   (cat([face, masked face]) in [0,1]; not modified)
  *   audio    fp32 [batch,32,32,32]    (HuBERT window; not modified)
  *   out      fp32 [batch,3,160,160] in (0,1), or uint8 [batch,160,160,3] with CASYNC_F_OUT_U8_HWC
- *   workspace  >= casync_workspace_bytes(plan, batch) bytes, 256-byte aligned, device memory */
+ *   workspace  >= casync_workspace_bytes(plan, batch) bytes, 256-byte aligned, device memory
+ * Asynchronous: enqueues on `stream` and returns.  Batches of 24 frames or more are additionally spread over
+ * plan-owned streams that are forked from and joined to `stream` (stream order is what the caller observes).  The second
+ * call with the same (x, audio, out, workspace, batch, flags) is captured into a CUDA graph and later calls with that
+ * key replay it; the buffers' CONTENTS may change freely between calls.  One call in flight per plan. */
 CASYNC_API int casync_forward(const casync_plan *plan, const float *x_nchw, const float *audio, void *out, void *workspace,
                    int batch, unsigned flags, void *stream);
 
@@ -94,7 +98,8 @@ CASYNC_API int casync_forward_profiled(const casync_plan *plan, const float *x_n
                                        void *workspace, int batch, unsigned flags, void *stream,
                                        casync_launch_record *recs, int max_recs, int *n_recs);
 
-/* Stage activations left in `workspace` by the last casync_forward with batch <= casync_chunk_frames():
+/* Stage activations left in `workspace` by the last casync_forward with batch <= casync_chunk_frames() and below the
+ * two-lane split threshold (24 frames; CASYNC_SPLIT=0 lifts it):
  * bf16 row-major [rows, cols] with leading dimension `ld` (elements) at byte `offset` (NHWC: rows =
  * batch*H*W pixels).  Names: x1..x5, audio, tx, ox0..ox3, kx, fuse, up1..up4 (oracle STAGE_NAMES). */
 CASYNC_API int casync_stage_view(const casync_plan *plan, int batch, const char *name, size_t *offset, int64_t *rows,
