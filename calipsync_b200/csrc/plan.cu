@@ -875,6 +875,7 @@ void casync_plan_destroy(casync_plan* plan) {
   }
   if (plan) chain_dbg_report();
   if (plan) {
+    cudaDeviceSynchronize();   // replays / lanes of the last forward may still be running
     for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     plan->graphs.clear();
   }
