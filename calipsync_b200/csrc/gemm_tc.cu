@@ -55,9 +55,15 @@ struct Cfg {
                                    : 2 * kAccCols <= 256 ? 256 : 512;   // tcgen05.alloc wants a power of two
 };
 
-template <int BN, bool DWE>
+// EPI selects the epilogue at compile time, so that its arithmetic is straight-line code (with run-time flags every
+// 8-column group was a chain of LDS -> dependent FADD with a branch between every small block: measured 5.5-10 us of a
+// 20-30 us launch):  0 bias (+ LeakyReLU)   1 + skip added after the activation (InvertedResidual)
+//                    2 + scaled residual before the activation (fc2, b_1)   3 everything by run-time flags (kv, bn7)
+enum : int { EPI_PLAIN = 0, EPI_RES_POST = 1, EPI_RES_PRE = 2, EPI_GENERIC = 3 };
+template <int BN, bool DWE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
   using C = Cfg<BN, DWE>;
+  constexpr bool kGen = EPI == EPI_GENERIC;
   constexpr int S = C::S;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -232,12 +238,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
       // residual rows (a launch uses res_pre or res_post, never both): the first 32-column chunk is requested BEFORE
       // waiting for the accumulator, so its latency hides behind the tile's main loop; later chunks are prefetched
       // one chunk ahead, behind the TMEM load + arithmetic of the current chunk
-      const __nv_bfloat16* rsrc = p.res_pre ? p.res_pre + (size_t)m * p.ld_rpre : p.res_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
+      const bool has_pre = kGen ? p.res_pre != nullptr : EPI == EPI_RES_PRE;
+      const bool has_post = kGen ? p.res_post != nullptr : EPI == EPI_RES_POST;
+      const bool has_ps = kGen ? p.post_scale != nullptr : false;
+      const bool has_vt = kGen ? (p.vt && n0 >= p.vt_col0) : false;
+      const float slope = p.leaky ? kLeaky : 1.0f;   // max(v, 1 * v) == v: LeakyReLU on / off without a branch
+      const __nv_bfloat16* rsrc = has_pre ? p.res_pre + (size_t)m * p.ld_rpre : has_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
       uint4 rnext[4];
       auto fetch_res = [&](int c0) {
+        if constexpr (EPI != EPI_PLAIN) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          rnext[g] = (rsrc && row_ok) ? *reinterpret_cast<const uint4*>(rsrc + n0 + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+          for (int g = 0; g < 4; ++g)
+            rnext[g] = (rsrc && row_ok) ? *reinterpret_cast<const uint4*>(rsrc + n0 + c0 + 8 * g) : make_uint4(0, 0, 0, 0);
+        }
       };
       if (cbeg < cend) fetch_res(cbeg);
       mbar_wait(acc_full(ab), (t >> 1) & 1);
@@ -249,9 +262,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
         uint32_t acc[32];
         tmem_ld32(trow + c0, acc);
         uint4 rcur[4];
+        if constexpr (EPI != EPI_PLAIN) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-        if (c0 + 32 < cend) fetch_res(c0 + 32);
+          for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+          if (c0 + 32 < cend) fetch_res(c0 + 32);
+        }
         tmem_ld_wait32(acc);
         T(13);
         if (row_ok) {
@@ -264,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
-            if (p.res_pre) {
+            if (has_pre) {
               const uint32_t* pr = &rcur[g].x;
               const float4 s0 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g);
               const float4 s1 = *reinterpret_cast<const float4*>(ev + 256 + c0 + 8 * g + 4);
@@ -275,11 +290,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
                 v[2 * q + 1] += ss[2 * q + 1] * bf16_hi(pr[q]);
               }
             }
-            if (p.leaky) {
+            if constexpr (kGen) {
+              if (p.leaky) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
+                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], slope * v[q]);
             }
-            if (p.res_post) {
+            if (has_post) {
               const uint32_t* pr = &rcur[g].x;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
                 v[2 * q + 1] += bf16_hi(pr[q]);
               }
             }
-            if (p.post_scale) {
+            if (has_ps) {
               const float4 s0 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g);
               const float4 s1 = *reinterpret_cast<const float4*>(ev + 512 + c0 + 8 * g + 4);
               const float4 t0 = *reinterpret_cast<const float4*>(ev + 768 + c0 + 8 * g);
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
                 v[q] = fmaxf(v[q], kLeaky * v[q]);
               }
             }
-            if (p.vt && n0 >= p.vt_col0) {   // transposed store of a value projection (see GemmArgs::vt)
+            if (has_vt) {   // transposed store of a value projection (see GemmArgs::vt)
               const int frame = m / 100, key = m - frame * 100;
               const int colv = n + 8 * g - p.vt_col0;   // j * 512 + channel
               __nv_bfloat16* dst = p.vt + ((size_t)frame * 2048 + colv) * 128 + key;
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
           }
         }
         T(14);
-        if (!(p.vt && n0 >= p.vt_col0)) {
+        if (!has_vt) {
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -540,7 +560,7 @@ int gemm_num_sms() { return g_num_sms; }
 
 namespace {
 
-template <int BN, bool DWE = false>
+template <int BN, bool DWE = false, int EPI = EPI_GENERIC>
 int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   const int tile_rows = DWE ? a.dw_w * a.dw_w : kBM;
   const int tiles = (a.N / BN) * ((a.M + tile_rows - 1) / tile_rows);
@@ -553,13 +573,32 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     const int e = gemm_encode_map(&tm, a.A, a.M, a.K, a.lda, kBM, true);
     if (e) return e;
   }
-  return (int)launch_pdl(gemm_tc_kernel<BN, DWE>, dim3(grid), dim3(kThreads), Cfg<BN, DWE>::kSmem, stream, a, tm);
+  return (int)launch_pdl(gemm_tc_kernel<BN, DWE, EPI>, dim3(grid), dim3(kThreads), Cfg<BN, DWE>::kSmem, stream, a, tm);
 }
 
-template <int BN, bool DWE = false>
-int set_attr() {
-  return (int)cudaFuncSetAttribute(gemm_tc_kernel<BN, DWE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int BN, bool DWE, int EPI>
+int set_attr1() {
+  return (int)cudaFuncSetAttribute(gemm_tc_kernel<BN, DWE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg<BN, DWE>::kSmem);
+}
+template <int BN>
+int set_attr() {
+  return set_attr1<BN, false, EPI_PLAIN>() | set_attr1<BN, false, EPI_RES_POST>() | set_attr1<BN, false, EPI_RES_PRE>() |
+         set_attr1<BN, false, EPI_GENERIC>();
+}
+// the epilogue variant a launch needs (see gemm_tc_kernel)
+int epi_of(const GemmArgs& a) {
+  if (a.post_scale || a.vt || (a.res_pre && a.res_post)) return EPI_GENERIC;
+  return a.res_pre ? EPI_RES_PRE : a.res_post ? EPI_RES_POST : EPI_PLAIN;
+}
+template <int BN>
+int launch_bn(const GemmArgs& a, cudaStream_t stream) {
+  switch (epi_of(a)) {
+    case EPI_PLAIN: return launch_cfg<BN, false, EPI_PLAIN>(a, stream);
+    case EPI_RES_POST: return launch_cfg<BN, false, EPI_RES_POST>(a, stream);
+    case EPI_RES_PRE: return launch_cfg<BN, false, EPI_RES_PRE>(a, stream);
+    default: return launch_cfg<BN, false, EPI_GENERIC>(a, stream);
+  }
 }
 
 // work-per-SM proxy: waves of tiles x (per-tile cost ~ A bytes + B bytes per k-block, the L2->smem traffic)
@@ -591,7 +630,7 @@ int gemm_init() {
   e |= set_attr<128>();
   e |= set_attr<192>();
   e |= set_attr<256>();
-  e |= set_attr<256, true>();
+  e |= set_attr1<256, true, EPI_PLAIN>();
   return e;
 }
 
@@ -603,7 +642,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     if (a.amode != A_PLAIN || a.N % 256 != 0 || px < 1 || px > kHidTileRows || a.M % px != 0 || !a.dwp || a.ldc != a.N ||
         a.res_pre || a.res_post || a.post_scale || a.vt || ((uintptr_t)a.dwp & 15))
       return (int)cudaErrorInvalidValue;
-    return launch_cfg<256, true>(a, stream);
+    return launch_cfg<256, true, EPI_PLAIN>(a, stream);
   }
   const long mt = (a.M + kBM - 1) / kBM;
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
@@ -618,11 +657,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     }
   }
   switch (best) {
-    case 256: return launch_cfg<256>(a, stream);
-    case 192: return launch_cfg<192>(a, stream);
-    case 128: return launch_cfg<128>(a, stream);
-    case 64: return launch_cfg<64>(a, stream);
-    default: return launch_cfg<32>(a, stream);
+    case 256: return launch_bn<256>(a, stream);
+    case 192: return launch_bn<192>(a, stream);
+    case 128: return launch_bn<128>(a, stream);
+    case 64: return launch_bn<64>(a, stream);
+    default: return launch_bn<32>(a, stream);
   }
 }
 
