@@ -307,22 +307,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
       if constexpr (NCOL == 64) tmem_ld32(tsrc + 32, accB);   // in flight while the first half is converted
 #endif
       auto convert = [&](const uint32_t* acc, int cc) {
+        // bias loads first, stores last: a shared-memory load cannot move above an earlier shared-memory store that
+        // might alias, so loading the bias per 8-column group serialised the groups (LDS -> FADD -> ... -> STS -> LDS)
+        float4 bq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bq[i] = lds_f4(sB1 + (c * 64 + col0 + cc + 4 * i) * 4);
+        uint32_t o[4][4];
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const float bv[8] = {bq[2 * g8].x, bq[2 * g8].y, bq[2 * g8].z, bq[2 * g8].w,
+                               bq[2 * g8 + 1].x, bq[2 * g8 + 1].y, bq[2 * g8 + 1].z, bq[2 * g8 + 1].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {   // bias in fp32, one rounding to bf16, LeakyReLU on the packed pair
+            __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(acc[g8 * 8 + 2 * j]) + bv[2 * j],
+                                                     __uint_as_float(acc[g8 * 8 + 2 * j + 1]) + bv[2 * j + 1]);
+            v = __hmax2(v, __hmul2(v, kslope));
+            o[g8][j] = inside ? *reinterpret_cast<uint32_t*>(&v) : 0u;
+          }
+        }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const int col = col0 + cc + g8 * 8;
-          uint32_t o[4] = {0u, 0u, 0u, 0u};
-          if (inside) {
-            const float4 ba = lds_f4(sB1 + (c * 64 + col) * 4), bb = lds_f4(sB1 + (c * 64 + col) * 4 + 16);
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {   // bias in fp32, one rounding to bf16, LeakyReLU on the packed pair
-              __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(acc[g8 * 8 + 2 * j]) + bv[2 * j],
-                                                       __uint_as_float(acc[g8 * 8 + 2 * j + 1]) + bv[2 * j + 1]);
-              v = __hmax2(v, __hmul2(v, kslope));
-              o[j] = *reinterpret_cast<uint32_t*>(&v);
-            }
-          }
-          sts128(hid + ((((uint32_t)col >> 3) ^ r7) << 4), o[0], o[1], o[2], o[3]);
+          sts128(hid + ((((uint32_t)col >> 3) ^ r7) << 4), o[g8][0], o[g8][1], o[g8][2], o[g8][3]);
         }
       };
       convert(accA, 0);

@@ -271,6 +271,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
         T(13);
         if (row_ok) {
           const int n = n0 + c0;
+          // all arithmetic first, the four staging stores after it: a shared-memory load (bias / scale vectors) cannot
+          // be scheduled above an earlier shared-memory store that might alias, so store-per-group serialised the groups
+          // (only where registers allow: the scaled-residual and generic variants keep one store per group -- measured)
+          constexpr bool kDefer = EPI == EPI_PLAIN || EPI == EPI_RES_POST;
+          uint4 og[kDefer ? 4 : 1];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {  // 8 columns per group -> one 16 B store
             float v[8];
@@ -327,13 +332,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
 #pragma unroll
               for (int q = 0; q < 8; ++q) dst[q * 128] = __float2bfloat16_rn(v[q]);
             } else {
-              uint4 o;
+              uint4& o = og[kDefer ? g : 0];
               o.x = pack_bf16(v[0], v[1]);
               o.y = pack_bf16(v[2], v[3]);
               o.z = pack_bf16(v[4], v[5]);
               o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+              if constexpr (!kDefer) *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
             }
+          }
+          if constexpr (kDefer) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = og[g];
           }
         }
         T(14);
