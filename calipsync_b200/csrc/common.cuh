@@ -74,8 +74,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for up to its time hint)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifndef CASYNC_MBAR_SLEEP_NS
+#define CASYNC_MBAR_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+    if (CASYNC_MBAR_SLEEP_NS > 0) asm volatile("nanosleep.u32 %0;" ::"n"(CASYNC_MBAR_SLEEP_NS));
+  }
+}
+
+// Wait with back-off: a warp that polls try_wait in a tight loop keeps issuing (measured on the strip kernel: 42 % of
+// all executed instructions were mbarrier polls of roles that were a whole tile ahead), taking issue slots from the
+// warps that do the work.  nanosleep parks the warp; use for waits that are normally long (not on the critical path).
+template <int NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+    asm volatile("nanosleep.u32 %0;" ::"n"(NS));
   }
 }
 

@@ -13,6 +13,7 @@
 #include "fused_ir.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "strip_ir.cuh"
 
 using namespace casync;
 typedef __nv_bfloat16 bf16;
@@ -205,6 +206,9 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
+  bool strip_ir = true;              // strip-streaming fused blocks (strip_ir.cu); CASYNC_STRIP=0 falls back to fused_ir.cu
+  std::vector<float> ir_b1, ir_b2;   // host copies of the folded-BN biases b1 / b2 of every InvertedResidual (128 floats each,
+                                    // zero padded): the strip kernel takes them as kernel parameters
   bool dw_epi = false;              // CASYNC_DWEPI=1: 10x10 blocks run the depthwise 3x3 in the epilogue of the first 1x1
                                     // conv (7 launches fewer, bit-exact).  Measured neutral at batch 64 (2.195 vs 2.193
                                     // ms: 31 us per fused launch against 22 + 17, but the depthwise pass now sits on
@@ -420,6 +424,27 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   const IrDef& d = kIr[idx];
   const std::string pre = std::string(d.name) + "|";
   const int hid = 2 * d.cin, H = d.h_in, Ho = d.stride == 2 ? H / 2 : H;
+  if (p->fuse_ir && p->strip_ir && !post_s && ldc == d.cout &&
+      strip_ir_supported(d.cin, d.cout, H, d.stride, up_low != nullptr, d.res)) {
+    StripArgs f{};
+    f.in = in;
+    f.low = up_low;
+    f.out = out;
+    f.W1 = p->w<uint8_t>(pre + "w1");
+    f.W2 = p->w<uint8_t>(pre + "w2");
+    f.wdp = p->w<uint8_t>(pre + "wdp");
+    f.batch = batch;
+    f.dbg = (p->phase_dbg && p->phase_dbg_ir == idx) ? p->phase_dbg : nullptr;
+    memcpy(f.b1, &p->ir_b1[(size_t)idx * 128], sizeof f.b1);
+    memcpy(f.b2, &p->ir_b2[(size_t)idx * 128], sizeof f.b2);
+    CK(chain_flush(p, st));
+    CK(launch_strip_ir(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res,
+                       g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms, st));
+    const double px_in = (double)batch * H * H, px_out = (double)batch * Ho * Ho;
+    prof_mark((short_name(d.name) + ".strip").c_str(), 2.0 * px_in * d.cin * hid + 18.0 * px_out * hid + 2.0 * px_out * hid * d.cout,
+              2.0 * (px_in * d.cin * (up_low ? 0.625 : 1.0) + px_out * d.cout * (d.res ? 2 : 1)));
+    return 0;
+  }
   if (p->fuse_ir && !post_s && ldc == d.cout && fused_ir_supported(d.cin, d.cout, d.stride, up_low != nullptr, d.res)) {
     FusedArgs f{};
     f.in = in;
@@ -790,6 +815,15 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   memcpy(&p->inc, hb + offsets[entry_index("inc.inconv.0|inc")], sizeof(IncParams));
   memcpy(&p->outc, hb + offsets[entry_index("outc|outc")], sizeof(OutcParams));
   memcpy(p->gamma, hb + offsets[entry_index("attention_blocks|gamma")], sizeof p->gamma);
+  p->ir_b1.assign((size_t)kNumIr * 128, 0.f);
+  p->ir_b2.assign((size_t)kNumIr * 128, 0.f);
+  for (int i = 1; i < kNumIr; ++i) {
+    const IrDef& d = kIr[i];
+    if (2 * d.cin > 128 || d.cout > 128) continue;
+    const std::string pre = std::string(d.name) + "|";
+    memcpy(&p->ir_b1[(size_t)i * 128], hb + offsets[entry_index(pre + "b1")], (size_t)2 * d.cin * 4);
+    memcpy(&p->ir_b2[(size_t)i * 128], hb + offsets[entry_index(pre + "b2")], (size_t)d.cout * 4);
+  }
   {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -797,13 +831,14 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   }
   if (const char* c = getenv("CASYNC_PHASE_DBG")) {   // developer aid: per-phase cycle counters of one fused block
     p->phase_dbg_ir = atoi(c);
-    if (cudaMalloc(&p->phase_dbg, 128) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 128);
+    if (cudaMalloc(&p->phase_dbg, 256) == cudaSuccess) cudaMemset(p->phase_dbg, 0, 256);
   }
   if (const char* c = getenv("CASYNC_GEMM_DBG")) {
     g_gemm_dbg_match = c;
     if (cudaMalloc(&g_gemm_dbg, 128) == cudaSuccess) cudaMemset(g_gemm_dbg, 0, 128);
   }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
+  if (const char* c = getenv("CASYNC_STRIP")) p->strip_ir = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_DWEPI")) p->dw_epi = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_CHAIN")) p->use_chain = atoi(c) > 0;        // opt in to layer-program launches
   if (const char* c = getenv("CASYNC_NO_CHAIN")) p->use_chain = !(atoi(c) > 0);   // (dev harness spelling)
@@ -842,6 +877,28 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
 }
 
 void casync_plan_destroy(casync_plan* plan) {
+  if (plan && plan->phase_dbg && plan->strip_ir && plan->phase_dbg_ir > 0 && plan->phase_dbg_ir < kNumIr &&
+      strip_ir_supported(kIr[plan->phase_dbg_ir].cin, kIr[plan->phase_dbg_ir].cout, kIr[plan->phase_dbg_ir].h_in,
+                         kIr[plan->phase_dbg_ir].stride, plan->phase_dbg_ir >= IR_UP && !((plan->phase_dbg_ir - IR_UP) & 1),
+                         kIr[plan->phase_dbg_ir].res)) {
+    unsigned long long h[32] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, plan->phase_dbg, 256, cudaMemcpyDeviceToHost);
+    const char* names[19] = {"I1:wait_a1full", "I1:wait_d1free", "I1:issue", "I2:wait_a2full", "I2:wait_d2free", "I2:issue",
+                             "P:wait_a1free", "P:issue", "P:land+arrive", "D:wait_d1full", "D:wait_hidfree", "D:work",
+                             "W:row", "W:wait_go", "W:publish", "W:loop", "E:prefetch", "E:wait_d2full", "E:work"};
+    const int lo[6] = {0, 3, 6, 9, 12, 16}, hi[6] = {3, 6, 9, 12, 16, 19};
+    fprintf(stderr, "[casync strip dbg] ir %d (share of each role's own time):\n", plan->phase_dbg_ir);
+    for (int r = 0; r < 6; ++r) {
+      double tot = 0;
+      for (int i = lo[r]; i < hi[r]; ++i) tot += (double)h[i];
+      fprintf(stderr, "   ");
+      for (int i = lo[r]; i < hi[r]; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
+      fprintf(stderr, "  [%.3g cycles]\n", tot);
+    }
+    cudaFree(plan->phase_dbg);
+    plan->phase_dbg = nullptr;
+  }
   if (plan && plan->phase_dbg) {
     unsigned long long h[16] = {0};
     cudaDeviceSynchronize();
@@ -918,7 +975,8 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
     const IrDef& d = kIr[i];
     const bool up = i >= IR_UP && !((i - IR_UP) & 1);
     const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) &&
-                       fused_ir_supported(d.cin, d.cout, d.stride, up, d.res);
+                       (fused_ir_supported(d.cin, d.cout, d.stride, up, d.res) ||
+                        (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
     const bool dwe = plan->dw_epi && !plan->use_chain && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
     per_chunk += fused ? 1 : dwe ? 2 : 3;
   }

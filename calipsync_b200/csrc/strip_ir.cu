@@ -1,0 +1,718 @@
+// Strip-streaming fused InvertedResidual (module/unet.py:8-40) for the high-resolution blocks (hidden width <= 128):
+//   pw1 (tcgen05) -> BN+leaky -> depthwise 3x3 (CUDA cores, vertical sliding window) -> BN+leaky -> pw2 (tcgen05)
+//   -> BN+leaky (+ skip)            -- the x2-expanded hidden tensor never leaves the SM.
+//
+// Geometry.  A frame is cut into S = W/SW vertical strips of SW output columns; a strip is a raster of (W+2) "padded"
+// rows x WW = SW+2 hidden columns (one halo column / row each side = the zero padding of the depthwise conv or the
+// neighbouring strip).  All (frame, strip, padded row) triples form ONE global list of NG = B*S*(W+2) rows; CTA i owns
+// the contiguous range [G0, G1) of it as *top rows*: it computes the hidden rows G0 .. G1+1 (2 rows of recompute per
+// CTA, < 1 %) and emits the output row whose 3x3 window starts at each top row G (top rows with hy >= W are the
+// strip's halo and emit nothing).  So there is no vertical halo recompute, and every CTA gets the same amount of work
+// whatever the batch.
+//
+// Streams.  Hidden positions q = (row - G0)*WW + hx are processed in tiles of 128 consecutive positions (one UMMA M
+// tile); output positions m = (n-th valid output row)*SW + ox likewise.  Warp-specialised roles, linked by mbarriers:
+//
+//   producers (4 warps)  A1[t]  <- global: one hidden position per thread, cp.async (zero fill outside the image);
+//                                  decoder: bilinear x2 of the low-res tensor computed on the fly + skip (unet.py:90-96)
+//   issuer 1 (1 thread)  D1[t]  =  A1[t] . W1^T                       tcgen05.mma M128 N=CH K16      -> TMEM fp32
+//   drain (8 warps)      HID[q] =  leaky(D1 + b1) as bf16 (0 outside the image: the depthwise conv zero-pads the
+//                                  HIDDEN tensor, unet.py:21-27) -> position ring in shared memory (3 tiles)
+//   depthwise (<=8 warps) thread = (4 channels, C adjacent output columns); walks DOWN the strip keeping the 3 x (C+2)
+//                                  window in registers: every hidden value is loaded 1 + 2/C times, taps never reloaded
+//                        A2[m]  =  leaky(dw3x3(HID) + bd)  bf16, SWIZZLE_128B rows = output positions
+//   issuer 2 (1 thread)  D2[k]  =  A2[k] . W2^T                       tcgen05.mma M128 N=COUT K16
+//   epilogue (4 warps)   out    =  leaky(D2 + b2) (+ x)  -> global NHWC bf16
+#include "strip_ir.cuh"
+
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+namespace casync {
+
+namespace {
+
+// Warp ranges of the roles.  The SM's warp arbiter favours high warp ids, so the depthwise warps (the longest role) sit
+// at the top and the roles that mostly poll at the bottom.  TMEM lane quarter = warp % 4: every range starts at a
+// multiple of 4.
+#ifndef STRIP_WARP_ORDER
+#define STRIP_WARP_ORDER 1
+#endif
+#if STRIP_WARP_ORDER
+constexpr int kIssWarp0 = 0, kEpiWarp0 = 4, kDrainWarp0 = 8, kProdWarp0 = 16, kDwWarp0 = 20;
+#else
+constexpr int kProdWarp0 = 0, kDrainWarp0 = 4, kDwWarp0 = 12, kEpiWarp0 = 20, kIssWarp0 = 24;
+#endif
+constexpr int kThreads = 28 * 32;   // 7 warpgroups: setmaxnreg moves registers between them
+constexpr int kRing = 384;       // hidden positions kept in shared memory: 3 tiles
+constexpr int kTileB = 16384;    // 128 rows x 128 B
+#ifndef STRIP_SLEEP_NS
+#define STRIP_SLEEP_NS 64
+#endif
+constexpr int kSleepNs = STRIP_SLEEP_NS;   // back-off of the roles that run ahead (producers, drain, epilogue, issuers)
+
+template <int CIN_, int COUT_, int W_, int SW_, int C_, bool UPCAT_, bool RES_>
+struct SCfg {
+  static constexpr int CIN = CIN_, COUT = COUT_, W = W_, SW = SW_, C = C_;
+  static constexpr bool UPCAT = UPCAT_, RES = RES_;
+  static constexpr int CH = 2 * CIN, NQ = CH / 4, WW = SW + 2, S = W / SW, HP = W + 2;
+  static constexpr int NKB2 = CH / 64, NCG = SW / C, CGW = 32 / NQ, DWW = NCG / CGW, DWT = DWW * 32;
+  static constexpr int RPT = 128 / SW;              // output rows per A2 tile (RPT * SW <= 128 positions used)
+  static constexpr int PB = CH * 2;                 // bytes per hidden position
+  static constexpr int SLOTB = NKB2 * kTileB;       // one A2 tile
+  static constexpr int oA1 = 0;
+  static constexpr int oHID = oA1 + 2 * kTileB;
+  static constexpr int oA2 = oHID + kRing * PB;
+  static constexpr int oW1 = oA2 + 2 * SLOTB;
+  static constexpr int oW2 = oW1 + CH * 128;
+  static constexpr int oMETA = oW2 + NKB2 * COUT * 128;
+  static constexpr int oBAR = oMETA + 4 * 128;
+  static constexpr int kSmem = oBAR + 512 + 1024;
+  static constexpr uint32_t kWeightBytes = CH * 128 + NKB2 * COUT * 128;
+  static_assert(CIN == 32 || CIN == 64, "one k-block of input channels");
+  static_assert(SW % C == 0 && W % SW == 0 && SW % 8 == 0, "strip geometry");
+  static_assert(NCG % CGW == 0 && DWW >= 1 && DWW <= 8 && RPT >= 1, "depthwise warps");
+  static_assert(3 * WW <= 257, "3-tile ring: the drain of tile t must never wait for a row the depthwise group still needs");
+  static_assert(2 * CH + 2 * COUT <= 512, "TMEM overflow");
+  static_assert(CH <= 128 && COUT <= 128, "biases travel as kernel parameters");
+  static_assert(!RES || CIN == COUT, "residual blocks keep the channel count");
+  static_assert(kSmem <= 232448, "shared memory overflow");
+};
+
+enum Bar : int {
+  B_W = 0, B_A1FULL = 1, B_A1FREE = 3, B_D1FULL = 5, B_D1FREE = 7, B_HIDFULL = 9, B_HIDFREE = 12, B_A2FULL = 15,
+  B_A2FREE = 17, B_D2FULL = 19, B_D2FREE = 21, B_COUNT = 23
+};
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+#ifndef STRIP_EXP
+#define STRIP_EXP 0   // developer timing experiments (wrong results): 1 no dw FMAs, 2 no drain math, 4 no bilinear, 8 no epilogue stores
+#endif
+#ifndef STRIP_DBG
+#define STRIP_DBG 0   // 1: per-role cycle counters (CASYNC_PHASE_DBG=<ir index>)
+#endif
+
+struct SmemView {
+  uint8_t* g;
+  uint32_t base;
+  template <class T>
+  __device__ __forceinline__ T& at(uint32_t addr) const { return *reinterpret_cast<T*>(g + (addr - base)); }
+};
+
+// Round trip through this thread's shared-memory scratch word with a volatile load: the value becomes opaque to
+// ptxas, which otherwise REMATERIALISES per-thread address constants (S2R tid -> shifts -> xor ...) inside the row
+// loop instead of keeping them in registers (measured: ~45 extra instructions per depthwise row).
+__device__ __forceinline__ uint32_t pin_reg(uint32_t x, uint32_t scratch) {
+  uint32_t y;
+  asm volatile("st.shared.u32 [%1], %2;\n\tld.volatile.shared.u32 %0, [%1];" : "=r"(y) : "r"(scratch), "r"(x) : "memory");
+  return y;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_s32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// leaky(acc + bias) for 8 consecutive accumulator columns starting at compile-time column COL -> 4 packed bf16x2
+template <int COL>
+__device__ __forceinline__ void bias_leaky8(const uint32_t* acc, const float* __restrict__ bias, const __nv_bfloat162 kslope,
+                                            uint32_t* o) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {   // bias in fp32 (constant-bank operand), one rounding to bf16, LeakyReLU on the packed pair
+    __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(acc[2 * j]) + bias[COL + 2 * j],
+                                             __uint_as_float(acc[2 * j + 1]) + bias[COL + 2 * j + 1]);
+    v = __hmax2(v, __hmul2(v, kslope));
+    o[j] = *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_constant__ StripArgs p) {
+  constexpr int CIN = C::CIN, COUT = C::COUT, W = C::W, SW = C::SW, NC = C::C, CH = C::CH, NQ = C::NQ, WW = C::WW,
+                S = C::S, HP = C::HP, H = C::W, NKB2 = C::NKB2, DWW = C::DWW, DWT = C::DWT, PB = C::PB, RPT = C::RPT;
+  constexpr bool UPCAT = C::UPCAT, RES = C::RES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const SmemView sm{smem_raw + (base - smem_u32(smem_raw)), base};
+  const uint32_t sA1 = base + C::oA1, sHID = base + C::oHID, sA2 = base + C::oA2, sW1 = base + C::oW1,
+                 sW2 = base + C::oW2, sMETA = base + C::oMETA, sBAR = base + C::oBAR;
+  auto bar = [&](int i) { return sBAR + 8u * i; };
+  const uint32_t tmem_slot = sBAR + 8u * B_COUNT;
+  const uint32_t sGO = tmem_slot + 8, sDONE = tmem_slot + 16;   // sync words of the depthwise group (see the agent warp)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+
+  if (tid == 0) {
+    mbar_init(bar(B_W), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(B_A1FULL + i), 128);
+      mbar_init(bar(B_A1FREE + i), 1);
+      mbar_init(bar(B_D1FULL + i), 1);
+      mbar_init(bar(B_D1FREE + i), 256);
+      mbar_init(bar(B_A2FULL + i), 1);
+      mbar_init(bar(B_A2FREE + i), 1);
+      mbar_init(bar(B_D2FULL + i), 1);
+      mbar_init(bar(B_D2FREE + i), 128);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(bar(B_HIDFULL + i), 256);
+      mbar_init(bar(B_HIDFREE + i), 1);
+    }
+    for (int i = 0; i < 10; ++i) sm.at<uint32_t>(sGO + 4 * i) = 0;   // go_rows, pad, dw_done[8]
+    fence_mbar_init();
+    mbar_arrive_expect_tx(bar(B_W), C::kWeightBytes);
+    bulk_g2s(sW1, p.W1, CH * 128, bar(B_W));
+    bulk_g2s(sW2, p.W2, NKB2 * COUT * 128, bar(B_W));
+  }
+  if (warp == kIssWarp0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  const uint32_t tD2 = tmem + 2 * CH;
+
+  // ---- this CTA's share of the global row list
+  const long long NG = (long long)p.batch * S * HP;
+  const int G0 = (int)(NG * blockIdx.x / gridDim.x), G1 = (int)(NG * (blockIdx.x + 1) / gridDim.x);
+  const int nrows = G1 - G0 + 2;                 // hidden rows computed here
+  const int NTh = (nrows * WW + 127) >> 7;       // hidden tiles
+  auto nvalid_before = [&](int G) { const int bs = G / HP, hy = G - bs * HP; return bs * H + (hy < H ? hy : H); };
+  const int V0 = nvalid_before(G0);
+  const int nvalid = nvalid_before(G1) - V0;     // output rows emitted here
+  const int NTo = (nvalid + RPT - 1) / RPT;      // output tiles: RPT rows of SW positions each
+  const int ntop = G1 - G0;
+  const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
+
+  long long tmark = STRIP_DBG && p.dbg ? clock64() : 0;
+  const bool timed = STRIP_DBG && p.dbg && lane == 0 && (warp == kProdWarp0 || warp == kDrainWarp0 || warp == kDwWarp0 ||
+                                            warp == kEpiWarp0 || warp == kIssWarp0 || warp == kIssWarp0 + 1);
+  auto T = [&](int slot) {
+    if (STRIP_DBG && timed) {
+      const long long now = clock64();
+      atomicAdd(p.dbg + slot, (unsigned long long)(now - tmark));
+      tmark = now;
+    }
+  };
+
+  if (warp >= kIssWarp0 && warp < kIssWarp0 + 4) {
+    // =========================================== MMA issuers ===================================================
+    setmaxnreg_dec<24>();
+    if (warp == kIssWarp0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, CH);
+      mbar_wait_sleep<kSleepNs>(bar(B_W), 0);
+      for (int t = 0; t < NTh; ++t) {
+        const int s = t & 1, ph = (t >> 1) & 1;
+        mbar_wait_sleep<kSleepNs>(bar(B_A1FULL + s), ph);
+        T(0);
+        mbar_wait_sleep<kSleepNs>(bar(B_D1FREE + s), ph ^ 1);
+        T(1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = umma_desc_sw128(sA1 + s * kTileB), bd = umma_desc_sw128(sW1);
+#pragma unroll
+          for (int ks = 0; ks < CIN / 16; ++ks) umma_bf16(tmem + s * CH, ad + 2 * ks, bd + 2 * ks, idesc1, ks != 0);
+          umma_commit(bar(B_D1FULL + s));
+          umma_commit(bar(B_A1FREE + s));
+        }
+        __syncwarp();
+        T(2);
+      }
+    } else if (warp == kIssWarp0 + 1) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, COUT);
+      mbar_wait_sleep<kSleepNs>(bar(B_W), 0);
+      for (int k = 0; k < NTo; ++k) {
+        const int s = k & 1, ph = (k >> 1) & 1;
+        mbar_wait_sleep<kSleepNs>(bar(B_A2FULL + s), ph);
+        T(3);
+        mbar_wait_sleep<kSleepNs>(bar(B_D2FREE + s), ph ^ 1);
+        T(4);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kb = 0; kb < NKB2; ++kb) {
+            const uint64_t ad = umma_desc_sw128(sA2 + kb * (2 * kTileB) + s * kTileB), bd = umma_desc_sw128(sW2 + kb * COUT * 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(tD2 + s * COUT, ad + 2 * ks, bd + 2 * ks, idesc2, (kb | ks) != 0);
+          }
+          umma_commit(bar(B_A2FREE + s));
+          umma_commit(bar(B_D2FULL + s));
+        }
+        __syncwarp();
+        T(5);
+      }
+    } else if (warp == kIssWarp0 + 2) {
+      // ----- sync agent of the depthwise group.  The depthwise warps never touch an mbarrier: each publishes the number
+      // of top rows it has finished (dw_done[w]) and polls ONE word (go_rows = top rows it may process).  This warp
+      // turns their progress into HIDFREE / A2FULL arrivals and the drain's / second GEMM's progress (HIDFULL, A2FREE)
+      // into go_rows, so the row loop carries no tile bookkeeping at all.
+      int sig_k = 0, freed_t = 0, ready_t = 0, acq_k = 0, go_pub = 0;
+      const int hy0 = G0 % HP, bs0 = G0 / HP;
+      for (;;) {
+        int d = lane < DWW ? (int)ld_acquire_s32(sDONE + 4 * lane) : 0x7fffffff;
+        d = __reduce_min_sync(0xffffffffu, d);
+        // output tiles completely written (the last one may be partial)
+        const int vd = nvalid_before(G0 + d) - V0;
+        const int tiles_done = d >= ntop ? NTo : vd / RPT;
+        if (sig_k < tiles_done) {
+          fence_proxy_async();   // the depthwise warps' A2 stores (observed through dw_done) -> async proxy (tcgen05.mma)
+          while (sig_k < tiles_done) {
+            if (lane == 0) mbar_arrive(bar(B_A2FULL + (sig_k & 1)));
+            ++sig_k;
+          }
+        }
+        // hidden tiles nobody will read again
+        while ((freed_t + 1) * 128 <= d * WW) {
+          if (lane == 0) mbar_arrive(bar(B_HIDFREE + freed_t % 3));
+          ++freed_t;
+        }
+        if (d >= ntop) break;
+        while (ready_t < NTh && mbar_test_wait(bar(B_HIDFULL + ready_t % 3), (ready_t / 3) & 1)) ++ready_t;
+        const int hr = ready_t >= NTh ? nrows : (ready_t * 128) / WW;   // complete hidden rows
+        while (acq_k < NTo && (acq_k < 2 || mbar_test_wait(bar(B_A2FREE + (acq_k & 1)), ((acq_k >> 1) & 1) ^ 1))) ++acq_k;
+        int ga = ntop;   // top rows allowed by A2: everything before the (acq_k * RPT)-th output row
+        if (acq_k < NTo) {
+          const int v = V0 + acq_k * RPT, bs = v / H, hy = v - bs * H;
+          ga = bs * HP + hy - G0;
+        }
+        int g = hr - 2;
+        g = g < ga ? g : ga;
+        g = g < ntop ? g : ntop;
+        if (g > go_pub) {
+          go_pub = g;
+          if (lane == 0) st_release_s32(sGO, (uint32_t)g);
+        }
+      }
+      (void)hy0; (void)bs0;
+    }
+  } else if (warp >= kProdWarp0 && warp < kProdWarp0 + 4) {
+    // =========================================== producers: A1[t] <- global ====================================
+    pdl_wait();   // activations only after the previous kernel is done (weights were requested above)
+    const int r = tid - kProdWarp0 * 32;
+    const uint32_t r7 = r & 7;
+    for (int t = 0; t <= NTh; ++t) {
+      if (t < NTh) {
+        const int s = t & 1;
+        if (t >= 2) mbar_wait_sleep<kSleepNs>(bar(B_A1FREE + s), ((t >> 1) & 1) ^ 1);
+        T(6);
+        const int q = t * 128 + r;
+        const int jrow = q / WW, hx = q - jrow * WW;
+        const int G = G0 + jrow;
+        const int bs = G / HP, hy = G - bs * HP;
+        const int b = bs / S, st = bs - b * S;
+        const int y = hy - 1, x = st * SW + hx - 1;
+        const bool inside = jrow < nrows && bs < p.batch * S && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+        sm.at<uint8_t>(sMETA + (t & 3) * 128 + r) = inside ? 1 : 0;
+        const uint32_t a1 = sA1 + s * kTileB + r * 128;
+        const size_t pix = inside ? ((size_t)b * H + y) * W + x : 0;
+        if constexpr (!UPCAT) {
+          const __nv_bfloat16* src = p.in + pix * CIN;
+#pragma unroll
+          for (int c = 0; c < CIN / 8; ++c) cp_async16(a1 + ((c ^ r7) << 4), src + c * 8, inside);
+        } else {
+          constexpr int C1 = CIN / 2;   // channels coming from the upsampled low-res tensor
+          constexpr int h = W / 2;
+          const __nv_bfloat16* sk = p.in + pix * C1;
+#pragma unroll
+          for (int c = C1 / 8; c < CIN / 8; ++c) cp_async16(a1 + ((c ^ r7) << 4), sk + (c * 8 - C1), inside);
+          // bilinear x2, align_corners=True: source coordinate = dst * (h-1)/(W-1)
+          const float sy = (float)(h - 1) / (float)(W - 1) * (float)(inside ? y : 0);
+          const float sx = (float)(h - 1) / (float)(W - 1) * (float)(inside ? x : 0);
+          const int y0 = (int)sy, x0 = (int)sx;
+          const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < h - 1 ? 1 : 0);
+          const float wy1 = sy - (float)y0, wy0 = 1.f - wy1, wx1 = sx - (float)x0, wx0 = 1.f - wx1;
+          const __nv_bfloat162 w00 = __float2bfloat162_rn(wy0 * wx0), w01 = __float2bfloat162_rn(wy0 * wx1),
+                               w10 = __float2bfloat162_rn(wy1 * wx0), w11 = __float2bfloat162_rn(wy1 * wx1);
+          const __nv_bfloat16* lb = p.low + (size_t)(inside ? b : 0) * h * h * C1;
+          const __nv_bfloat16* p00 = lb + (size_t)(y0 * h + x0) * C1;
+          const __nv_bfloat16* p01 = lb + (size_t)(y0 * h + x1) * C1;
+          const __nv_bfloat16* p10 = lb + (size_t)(y1 * h + x0) * C1;
+          const __nv_bfloat16* p11 = lb + (size_t)(y1 * h + x1) * C1;
+          constexpr int NB = C1 / 8;   // all chunks of the row at once (16 loads in flight)
+#pragma unroll
+          for (int c0 = 0; c0 < C1 / 8; c0 += NB) {
+            uint4 ta[NB], tb[NB], tc[NB], td[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+              ta[i] = tb[i] = tc[i] = td[i] = make_uint4(0, 0, 0, 0);
+              if (inside && !(STRIP_EXP & 4)) {
+                ta[i] = __ldg(reinterpret_cast<const uint4*>(p00 + (c0 + i) * 8));
+                tb[i] = __ldg(reinterpret_cast<const uint4*>(p01 + (c0 + i) * 8));
+                tc[i] = __ldg(reinterpret_cast<const uint4*>(p10 + (c0 + i) * 8));
+                td[i] = __ldg(reinterpret_cast<const uint4*>(p11 + (c0 + i) * 8));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+              const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ta[i]);
+              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&tb[i]);
+              const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&tc[i]);
+              const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&td[i]);
+              uint4 o;
+              __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                po[j] = __hfma2(w11, pd[j], __hfma2(w10, pc[j], __hfma2(w01, pb[j], __hmul2(w00, pa[j]))));
+              sm.at<uint4>(a1 + (((c0 + i) ^ r7) << 4)) = o;
+            }
+          }
+        }
+        cp_async_commit();
+        T(7);
+      }
+      if constexpr (UPCAT) {
+        // the skip rows were requested first and had the whole bilinear section to land: no deferral, so the first GEMM
+        // of this tile does not have to wait for the next tile's loads to be issued
+        if (t < NTh) {
+          cp_async_wait<0>();
+          fence_proxy_async();
+          mbar_arrive(bar(B_A1FULL + (t & 1)));
+          T(8);
+        }
+      } else if (t >= 1) {   // tile t-1 has landed once at most the newest group is still in flight
+        if (t < NTh) cp_async_wait<1>(); else cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(bar(B_A1FULL + ((t - 1) & 1)));
+        T(8);
+      }
+    }
+  } else if (warp >= kDrainWarp0 && warp < kDrainWarp0 + 8) {
+    // =========================================== drain: D1 -> HID ring =========================================
+    const int dwp = warp - kDrainWarp0, lg = dwp & 3, hw = dwp >> 2;   // TMEM lane quarter, column half
+    const int row = lg * 32 + lane;
+    constexpr int NCOL = CH / 2;   // columns per thread
+    for (int t = 0; t < NTh; ++t) {
+      const int b = t & 1;
+      mbar_wait_sleep<kSleepNs>(bar(B_D1FULL + b), (t >> 1) & 1);
+      T(9);
+      if (t >= 3) mbar_wait_sleep<kSleepNs>(bar(B_HIDFREE + t % 3), ((t / 3) & 1) ^ 1);
+      T(10);
+      const bool inside = sm.at<uint8_t>(sMETA + (t & 3) * 128 + row) != 0;
+      tc_fence_after();
+      const int q = t * 128 + row;
+      const int jrow = q / WW, hx = q - jrow * WW;
+      const uint32_t hid = sHID + (uint32_t)(q % kRing) * PB;
+      const uint32_t h7 = hx & 7;
+      const uint32_t tsrc = tmem + b * CH + hw * NCOL + ((uint32_t)(lg * 32) << 16);
+#pragma unroll
+      for (int cc = 0; cc < NCOL; cc += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tsrc + cc, acc);
+        tmem_ld_wait32(acc);
+        if (cc + 32 >= NCOL) {   // accumulator fully read: the next pw1 may overwrite it
+          tc_fence_before();
+          mbar_arrive(bar(B_D1FREE + b));
+        }
+        uint32_t o[4][4];
+        if (STRIP_EXP & 2) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) o[g8][jj] = acc[g8 * 8 + jj];
+        } else if (hw == 0) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (cc == 0) bias_leaky8<0>(acc + g8 * 8, p.b1 + g8 * 8, kslope, o[g8]);
+            else bias_leaky8<0>(acc + g8 * 8, p.b1 + 32 + g8 * 8, kslope, o[g8]);
+          }
+        } else {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (cc == 0) bias_leaky8<0>(acc + g8 * 8, p.b1 + NCOL + g8 * 8, kslope, o[g8]);
+            else bias_leaky8<0>(acc + g8 * 8, p.b1 + NCOL + 32 + g8 * 8, kslope, o[g8]);
+          }
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const uint32_t j = (uint32_t)(hw * NCOL + cc) / 8 + g8;   // 16-byte chunk of the position
+          const uint4 v = inside ? make_uint4(o[g8][0], o[g8][1], o[g8][2], o[g8][3]) : make_uint4(0, 0, 0, 0);
+          sm.at<uint4>(hid + ((j ^ h7) << 4)) = v;
+        }
+      }
+      mbar_arrive(bar(B_HIDFULL + t % 3));
+      T(11);
+    }
+  } else if (warp >= kDwWarp0 && warp < kDwWarp0 + 8) {
+    // =========================================== depthwise 3x3: HID -> A2 ======================================
+    setmaxnreg_inc<96>();
+    const int dt = tid - kDwWarp0 * 32;
+    if (dt < DWT) {
+      const int quad = dt % NQ, cg = dt / NQ, dwarp = dt >> 5;
+      const int col0 = cg * NC;
+      const uint32_t j = (uint32_t)quad >> 1, half8 = (quad & 1) * 8;
+      const uint32_t scratch = sA2 + (uint32_t)dt * 4;   // A2 is not written before the first row is complete
+      // hidden column hx = col0 + kx: byte offset inside a ring row segment (16-byte chunk j XOR-swizzled with hx & 7)
+      uint32_t off[NC + 2];
+#pragma unroll
+      for (int kx = 0; kx < NC + 2; ++kx)
+        off[kx] = pin_reg(kx * PB + ((j ^ ((uint32_t)(col0 + kx) & 7u)) << 4) + half8, scratch);
+      // A2 ([k-block][slot][128 rows][128 B], SWIZZLE_128B): row = slot * 128 + (row in tile) * SW + column; SW % 8 == 0,
+      // so the swizzle term (row & 7) = (col0 + c) & 7 never changes
+      uint32_t a2p[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        a2p[c] = pin_reg(sA2 + (uint32_t)(quad >> 4) * (2 * kTileB) + (uint32_t)(col0 + c) * 128u +
+                             (((((uint32_t)quad & 15u) >> 1) ^ ((uint32_t)(col0 + c) & 7u)) << 4) + half8, scratch);
+      const uint32_t hid0 = pin_reg(sHID, scratch), go_addr = pin_reg(sGO, scratch),
+                     done_addr = pin_reg(sDONE + 4 * dwarp, scratch);
+      __nv_bfloat162 wt[9][2], wbias[2];
+      {
+        const uint2* tp = reinterpret_cast<const uint2*>(p.wdp + (size_t)(quad >> 1) * 160 + half8);
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const uint2 w2 = __ldg(tp + t9 * 2);
+          wt[t9][0] = *reinterpret_cast<const __nv_bfloat162*>(&w2.x);
+          wt[t9][1] = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
+        }
+        const uint2 b2 = __ldg(tp + 18);
+        wbias[0] = *reinterpret_cast<const __nv_bfloat162*>(&b2.x);
+        wbias[1] = *reinterpret_cast<const __nv_bfloat162*>(&b2.y);
+      }
+      auto tap = [&](__nv_bfloat162* a, const uint2& v, const __nv_bfloat162* w) {
+        a[0] = __hfma2(w[0], *reinterpret_cast<const __nv_bfloat162*>(&v.x), a[0]);
+        a[1] = __hfma2(w[1], *reinterpret_cast<const __nv_bfloat162*>(&v.y), a[1]);
+      };
+      int o0 = col0;       // ring index of (next hidden row to load, column col0)
+      int go = 0;          // top rows this warp may process (cached copy of go_rows)
+      int jt = 0;          // top rows done
+      int hy = G0 % HP;
+      uint32_t arow = 0;   // byte offset of the current A2 row: (slot * 128 + row-in-tile * SW) * 128
+      uint32_t aslot = 0;  // byte offset of the current A2 slot (0 or one tile)
+      int rcnt = 0;        // output rows written into the current A2 tile
+      auto wait_go = [&](int need) {   // until go_rows > need
+        while (go <= need) {
+          go = (int)ld_acquire_s32(go_addr);
+          if (go <= need) asm volatile("nanosleep.u32 20;");
+        }
+      };
+      auto load_row = [&](uint2* dst) {
+        if (o0 + NC + 1 < kRing) {
+          const uint32_t rb = hid0 + (uint32_t)o0 * PB;
+#pragma unroll
+          for (int kx = 0; kx < NC + 2; ++kx) dst[kx] = sm.at<uint2>(rb + off[kx]);
+        } else {
+#pragma unroll
+          for (int kx = 0; kx < NC + 2; ++kx) {
+            int idx = o0 + kx;
+            if (idx >= kRing) idx -= kRing;
+            dst[kx] = sm.at<uint2>(hid0 + (uint32_t)idx * PB + (off[kx] - kx * PB));
+          }
+        }
+        o0 += WW;
+        if (o0 >= kRing) o0 -= kRing;
+      };
+      // one top row: load the window's bottom row, emit the output row (unless this top row is strip halo), publish
+      auto row_step = [&](const uint2* top, const uint2* mid, uint2* bot) {
+        T(15);
+        if (jt >= go) wait_go(jt);
+        T(13);
+        load_row(bot);
+        bool tile_end = false;
+        if (hy < H) {
+          __nv_bfloat162 a[NC][2];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            a[c][0] = wbias[0];
+            a[c][1] = wbias[1];
+          }
+          if (!(STRIP_EXP & 1)) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tap(a[c], top[c + kx], wt[kx]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tap(a[c], mid[c + kx], wt[3 + kx]);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tap(a[c], bot[c + kx], wt[6 + kx]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tap(a[c], bot[c], wt[0]);
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            a[c][0] = __hmax2(a[c][0], __hmul2(a[c][0], kslope));
+            a[c][1] = __hmax2(a[c][1], __hmul2(a[c][1], kslope));
+            sm.at<uint2>(a2p[c] + arow) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&a[c][0]), *reinterpret_cast<uint32_t*>(&a[c][1]));
+          }
+          arow += SW * 128;
+          if (++rcnt == RPT) {   // tile complete: next tile in the other slot
+            rcnt = 0;
+            aslot ^= (uint32_t)kTileB;
+            arow = aslot;
+            tile_end = true;
+          }
+        }
+        ++jt;
+        if (++hy == HP) hy = 0;
+        T(12);
+        // progress: a relaxed store is enough for the ring (the row's loads have been consumed by the FMAs above, in
+        // order); the row that completes an A2 tile publishes with fence.proxy.async + release so that the agent's
+        // A2FULL arrival orders the stores before the tcgen05.mma reads
+        __syncwarp();
+        if (tile_end || jt == ntop) {
+          fence_proxy_async();
+          if (lane == 0) st_release_s32(done_addr, (uint32_t)jt);
+        } else if (lane == 0) {
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(done_addr), "r"((uint32_t)jt) : "memory");
+        }
+        T(14);
+      };
+      uint2 r0[NC + 2], r1[NC + 2], r2[NC + 2];
+      wait_go(0);   // go_rows > 0 <=> hidden rows 0..2 are in the ring
+      load_row(r0);
+      load_row(r1);
+      while (jt + 3 <= ntop) {   // three rows per iteration: the window buffers rotate by name, not by moves
+        row_step(r0, r1, r2);
+        row_step(r1, r2, r0);
+        row_step(r2, r0, r1);
+      }
+      if (jt < ntop) {
+        row_step(r0, r1, r2);
+        if (jt < ntop) row_step(r1, r2, r0);
+      }
+      T(15);
+    }
+  } else {
+    // =========================================== epilogue: D2 -> global ========================================
+    pdl_wait();
+    const int row = (warp - kEpiWarp0) * 32 + lane;
+    for (int k = 0; k < NTo; ++k) {
+      const int s = k & 1;
+      const int rt = row / SW, ox = row - rt * SW;   // row of the tile -> (output row in tile, column)
+      const int n = k * RPT + rt;                     // ordinal of the output row
+      const bool valid = rt < RPT && n < nvalid;
+      const int v = V0 + n;
+      const int bs = v / H, hy = v - bs * H;
+      const int b = bs / S, st = bs - b * S;
+      const size_t pix = valid ? ((size_t)b * H + hy) * W + st * SW + ox : 0;
+      uint4 rr[RES ? COUT / 8 : 1];
+      if constexpr (RES) {
+#pragma unroll
+        for (int i = 0; i < COUT / 8; ++i)
+          rr[i] = valid ? __ldg(reinterpret_cast<const uint4*>(p.in + pix * CIN + i * 8)) : make_uint4(0, 0, 0, 0);
+      }
+      T(16);
+      mbar_wait_sleep<kSleepNs>(bar(B_D2FULL + s), (k >> 1) & 1);
+      T(17);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < COUT; cc += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tD2 + s * COUT + cc + ((uint32_t)((warp & 3) * 32) << 16), acc);
+        tmem_ld_wait32(acc);
+        if (cc + 32 >= COUT) {
+          tc_fence_before();
+          mbar_arrive(bar(B_D2FREE + s));
+        }
+        if (valid && !((STRIP_EXP & 8) && acc[0] != 0x12345u)) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float vv[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              vv[jj] = __uint_as_float(acc[g8 * 8 + jj]) + p.b2[cc + g8 * 8 + jj];
+              vv[jj] = fmaxf(vv[jj], kLeaky * vv[jj]);
+            }
+            if constexpr (RES) {   // skip = the block input at the same pixel, added after the activation (unet.py:38)
+              const uint32_t* pr = &rr[(cc >> 3) + g8].x;
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                vv[2 * jj] += bf16_lo(pr[jj]);
+                vv[2 * jj + 1] += bf16_hi(pr[jj]);
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + pix * COUT + cc + g8 * 8) =
+                make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]), pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
+          }
+        }
+      }
+      T(18);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kIssWarp0) tmem_dealloc(tmem, 512);
+}
+
+template <class C>
+int launch_t(const StripArgs& a, int num_sms, cudaStream_t st) {
+  static unsigned long long attr_devs = 0;   // per device: cudaFuncSetAttribute is a per-device setting
+  auto kfn = strip_ir_kernel<C>;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_devs >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    attr_devs |= 1ull << (dev & 63);
+  }
+  const long long NG = (long long)a.batch * C::S * C::HP;
+  long long grid = NG / 6;   // at least ~6 top rows per CTA (2 rows of recompute each)
+  if (grid < 1) grid = 1;
+  if (grid > num_sms) grid = num_sms;
+  return (int)launch_pdl(kfn, dim3((unsigned)grid), dim3(kThreads), C::kSmem, st, a);
+}
+
+}  // namespace
+
+// Instantiated where the strip kernel beats fused_ir.cu on B200 (batch 64, CUDA events): up4.0 216 vs 261 us, down1.1
+// 79 vs 99, up2.1 29.5 vs 31, audio conv1 17 vs 19.  The 32-channel residual blocks (up4.1 166 vs 141 us, up3.1 50 vs
+// 43) stay on the patch kernel: with 64 hidden channels the per-tile bookkeeping outweighs the saved halo work.
+#define STRIP_CASES(X)                                                         \
+  X(64, 32, 160, 32, 4, true, false)  /* up4.0 */                             \
+  X(64, 64, 80, 40, 5, false, true)   /* down1.1 */                           \
+  X(64, 64, 40, 40, 5, false, true)   /* up2.1 */                             \
+  X(32, 64, 32, 32, 2, false, false)  /* audio conv1 */
+#define STRIP_CASES_ALL(X)                                                     \
+  STRIP_CASES(X)                                                               \
+  X(32, 32, 160, 32, 2, false, true)  /* up4.1 */                             \
+  X(32, 32, 80, 40, 5, false, true)   /* up3.1 */
+
+static bool strip_all() {   // CASYNC_STRIP=2: also the instantiations that lose to the patch kernel (A/B runs)
+  static const bool all = getenv("CASYNC_STRIP") && atoi(getenv("CASYNC_STRIP")) >= 2;
+  return all;
+}
+
+bool strip_ir_supported(int cin, int cout, int W, int stride, bool upcat, bool res) {
+  if (stride != 1) return false;
+#define X(CIN_, COUT_, W_, SW_, C_, U_, R_) \
+  if (cin == CIN_ && cout == COUT_ && W == W_ && upcat == U_ && res == R_) return true;
+  if (strip_all()) {
+    STRIP_CASES_ALL(X)
+  } else {
+    STRIP_CASES(X)
+  }
+#undef X
+  return false;
+}
+
+int launch_strip_ir(const StripArgs& a, int cin, int cout, int W, int stride, bool upcat, bool res, int num_sms,
+                    cudaStream_t st) {
+  if (stride != 1) return -1;
+#define X(CIN_, COUT_, W_, SW_, C_, U_, R_)                                     \
+  if (cin == CIN_ && cout == COUT_ && W == W_ && upcat == U_ && res == R_)      \
+    return launch_t<SCfg<CIN_, COUT_, W_, SW_, C_, U_, R_>>(a, num_sms, st);
+  if (!strip_ir_supported(cin, cout, W, stride, upcat, res)) return -1;
+  STRIP_CASES_ALL(X)
+#undef X
+  return -1;
+}
+
+}  // namespace casync

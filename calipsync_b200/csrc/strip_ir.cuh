@@ -1,0 +1,25 @@
+// Strip-streaming fused InvertedResidual kernel (pw1 -> depthwise 3x3 -> pw2 in one launch); see strip_ir.cu.
+#pragma once
+#include "common.cuh"
+
+namespace casync {
+
+struct StripArgs {
+  const __nv_bfloat16* in;   // block input NHWC [B,W,W,cin]   (decoder: the skip tensor [B,W,W,cin/2])
+  const __nv_bfloat16* low;  // decoder only: low-res tensor [B,W/2,W/2,cin/2], bilinearly upsampled on the fly
+  __nv_bfloat16* out;        // NHWC [B,W/stride,W/stride,cout], dense
+  const uint8_t* W1;         // packed [k-block][2cin rows][128 B]
+  const uint8_t* W2;         // packed [k-block][cout rows][128 B]
+  const uint8_t* wdp;        // depthwise taps + folded-BN bias as bf16 [2cin/8][10][8]
+  int batch;
+  unsigned long long* dbg;   // optional per-role cycle counters (developer timing, CASYNC_PHASE_DBG)
+  float b1[128];             // folded-BN biases travel as kernel parameters: the drains add them straight from the
+  float b2[128];             // constant bank (no shared-memory loads, no registers)
+};
+
+// cin/cout/W/stride/upcat/res select the instantiation.  Returns -1 when the block shape has none, else 0 / cudaError.
+int launch_strip_ir(const StripArgs& a, int cin, int cout, int W, int stride, bool upcat, bool res, int num_sms,
+                    cudaStream_t st);
+bool strip_ir_supported(int cin, int cout, int W, int stride, bool upcat, bool res);
+
+}  // namespace casync
