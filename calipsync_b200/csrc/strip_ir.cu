@@ -45,7 +45,6 @@ constexpr int kIssWarp0 = 0, kEpiWarp0 = 4, kDrainWarp0 = 8, kProdWarp0 = 16, kD
 constexpr int kProdWarp0 = 0, kDrainWarp0 = 4, kDwWarp0 = 12, kEpiWarp0 = 20, kIssWarp0 = 24;
 #endif
 constexpr int kThreads = 28 * 32;   // 7 warpgroups: setmaxnreg moves registers between them
-constexpr int kRing = 384;       // hidden positions kept in shared memory: 3 tiles
 constexpr int kTileB = 16384;    // 128 rows x 128 B
 #ifndef STRIP_SLEEP_NS
 #define STRIP_SLEEP_NS 64
@@ -60,10 +59,12 @@ struct SCfg {
   static constexpr int NKB2 = CH / 64, NCG = SW / C, CGW = 32 / NQ, DWW = NCG / CGW, DWT = DWW * 32;
   static constexpr int RPT = 128 / SW;              // output rows per A2 tile (RPT * SW <= 128 positions used)
   static constexpr int PB = CH * 2;                 // bytes per hidden position
+  static constexpr int RINGT = CH <= 64 ? 6 : 3;    // hidden ring in 128-position tiles: what shared memory allows
+  static constexpr int kRing = RINGT * 128, NH = 2 * RINGT;   // positions; half-tile slots (credit granularity)
   static constexpr int SLOTB = NKB2 * kTileB;       // one A2 tile
   static constexpr int oA1 = 0;
   static constexpr int oHID = oA1 + 2 * kTileB;
-  static constexpr int oA2 = oHID + kRing * PB;
+  static constexpr int oA2 = oHID + RINGT * 128 * PB;
   static constexpr int oW1 = oA2 + 2 * SLOTB;
   static constexpr int oW2 = oW1 + CH * 128;
   static constexpr int oMETA = oW2 + NKB2 * COUT * 128;
@@ -73,7 +74,7 @@ struct SCfg {
   static_assert(CIN == 32 || CIN == 64, "one k-block of input channels");
   static_assert(SW % C == 0 && W % SW == 0 && SW % 8 == 0, "strip geometry");
   static_assert(NCG % CGW == 0 && DWW >= 1 && DWW <= 8 && RPT >= 1, "depthwise warps");
-  static_assert(3 * WW <= 257, "3-tile ring: the drain of tile t must never wait for a row the depthwise group still needs");
+  static_assert(3 * WW <= (RINGT - 1) * 128 + 64, "ring too small: the drain would wait for rows the depthwise group still needs");
   static_assert(2 * CH + 2 * COUT <= 512, "TMEM overflow");
   static_assert(CH <= 128 && COUT <= 128, "biases travel as kernel parameters");
   static_assert(!RES || CIN == COUT, "residual blocks keep the channel count");
@@ -81,8 +82,8 @@ struct SCfg {
 };
 
 enum Bar : int {
-  B_W = 0, B_A1FULL = 1, B_A1FREE = 3, B_D1FULL = 5, B_D1FREE = 7, B_HIDFULL = 9, B_HIDFREE = 12, B_A2FULL = 15,
-  B_A2FREE = 17, B_D2FULL = 19, B_D2FREE = 21, B_COUNT = 23
+  B_W = 0, B_A1FULL = 1, B_A1FREE = 3, B_D1FULL = 5, B_D1FREE = 7, B_A2FULL = 9, B_A2FREE = 11, B_D2FULL = 13,
+  B_D2FREE = 15, B_HIDFULL = 17, B_HIDFREE = 29, B_COUNT = 41   // HIDFULL / HIDFREE: one per half-tile slot (<= 12)
 };
 
 template <int N>
@@ -138,7 +139,8 @@ __device__ __forceinline__ void bias_leaky8(const uint32_t* acc, const float* __
 template <class C>
 __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_constant__ StripArgs p) {
   constexpr int CIN = C::CIN, COUT = C::COUT, W = C::W, SW = C::SW, NC = C::C, CH = C::CH, NQ = C::NQ, WW = C::WW,
-                S = C::S, HP = C::HP, H = C::W, NKB2 = C::NKB2, DWW = C::DWW, DWT = C::DWT, PB = C::PB, RPT = C::RPT;
+                S = C::S, HP = C::HP, H = C::W, NKB2 = C::NKB2, DWW = C::DWW, DWT = C::DWT, PB = C::PB, RPT = C::RPT,
+                kRing = C::kRing, NH = C::NH;
   constexpr bool UPCAT = C::UPCAT, RES = C::RES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
       mbar_init(bar(B_D2FULL + i), 1);
       mbar_init(bar(B_D2FREE + i), 128);
     }
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(bar(B_HIDFULL + i), 256);
+    for (int i = 0; i < NH; ++i) {
+      mbar_init(bar(B_HIDFULL + i), 128);   // the four drain warps of one half-tile
       mbar_init(bar(B_HIDFREE + i), 1);
     }
     for (int i = 0; i < 10; ++i) sm.at<uint32_t>(sGO + 4 * i) = 0;   // go_rows, pad, dw_done[8]
@@ -274,13 +276,13 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
           }
         }
         // hidden tiles nobody will read again
-        while ((freed_t + 1) * 128 <= d * WW) {
-          if (lane == 0) mbar_arrive(bar(B_HIDFREE + freed_t % 3));
+        while ((freed_t + 1) * 64 <= d * WW) {   // half-tiles
+          if (lane == 0) mbar_arrive(bar(B_HIDFREE + freed_t % NH));
           ++freed_t;
         }
         if (d >= ntop) break;
-        while (ready_t < NTh && mbar_test_wait(bar(B_HIDFULL + ready_t % 3), (ready_t / 3) & 1)) ++ready_t;
-        const int hr = ready_t >= NTh ? nrows : (ready_t * 128) / WW;   // complete hidden rows
+        while (ready_t < 2 * NTh && mbar_test_wait(bar(B_HIDFULL + ready_t % NH), (ready_t / NH) & 1)) ++ready_t;
+        const int hr = ready_t >= 2 * NTh ? nrows : (ready_t * 64) / WW;   // complete hidden rows
         while (acq_k < NTo && (acq_k < 2 || mbar_test_wait(bar(B_A2FREE + (acq_k & 1)), ((acq_k >> 1) & 1) ^ 1))) ++acq_k;
         int ga = ntop;   // top rows allowed by A2: everything before the (acq_k * RPT)-th output row
         if (acq_k < NTo) {
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
           go_pub = g;
           if (lane == 0) st_release_s32(sGO, (uint32_t)g);
         }
+        asm volatile("nanosleep.u32 20;");
       }
       (void)hy0; (void)bs0;
     }
@@ -395,9 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
     constexpr int NCOL = CH / 2;   // columns per thread
     for (int t = 0; t < NTh; ++t) {
       const int b = t & 1;
+      const int ht = 2 * t + (lg >> 1);   // this warp's half-tile (64 positions): the ring's credit granularity
       mbar_wait_sleep<kSleepNs>(bar(B_D1FULL + b), (t >> 1) & 1);
       T(9);
-      if (t >= 3) mbar_wait_sleep<kSleepNs>(bar(B_HIDFREE + t % 3), ((t / 3) & 1) ^ 1);
+      if (ht >= NH) mbar_wait_sleep<kSleepNs>(bar(B_HIDFREE + ht % NH), ((ht / NH) & 1) ^ 1);
       T(10);
       const bool inside = sm.at<uint8_t>(sMETA + (t & 3) * 128 + row) != 0;
       tc_fence_after();
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
           sm.at<uint4>(hid + ((j ^ h7) << 4)) = v;
         }
       }
-      mbar_arrive(bar(B_HIDFULL + t % 3));
+      mbar_arrive(bar(B_HIDFULL + ht % NH));
       T(11);
     }
   } else if (warp >= kDwWarp0 && warp < kDwWarp0 + 8) {
