@@ -32,6 +32,7 @@ SYMBOLS = [
     ("casync_audio_cnn", _I, [_P, _P, _P, _P, _I, _P]),
     ("casync_fusion_attention", _I, [_P, _P, _P, _P, _P, _I, _P]),
     ("casync_up_block", _I, [_P, _I, _P, _P, _P, _P, _I, _P]),
+    ("casync_up_first", _I, [_P, _I, _P, _P, _P, _P, _I, _P]),
 ]
 
 

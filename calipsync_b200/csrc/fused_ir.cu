@@ -653,13 +653,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_ir_kernel(const FusedArgs p
 template <int CIN, int COUT, int STRIDE, bool UPCAT, bool RES, int TILES, int A1BUFS, bool WS = false>
 int launch_t(const FusedArgs& a, cudaStream_t st) {
   using C = FCfg<CIN, COUT, STRIDE, TILES, A1BUFS, WS>;
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;   // the attribute is a per-device setting
   auto kfn = fused_ir_kernel<CIN, COUT, STRIDE, UPCAT, RES, TILES, A1BUFS, WS>;
   if (WS && !a.wdp) return (int)cudaErrorInvalidValue;
-  if (!attr_set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_devs >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_devs |= 1ull << (dev & 63);
   }
   const int Wo = a.W / STRIDE;
   const int NP = a.batch * ((Wo + C::TOW - 1) / C::TOW) * ((Wo + C::TOH - 1) / C::TOH);

@@ -646,7 +646,8 @@ int gemm_init() {
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
-  if (a.N % 32 != 0 || a.K % 64 != 0) return (int)cudaErrorInvalidValue;   // whole 64-channel k-blocks only
+  // partial k-blocks: the packed weights are zero-padded to 64, TMA zero-fills columns >= K, gathers test k < K
+  if (a.N % 32 != 0 || a.K % 8 != 0) return (int)cudaErrorInvalidValue;
   if (a.dw_epi) {   // depthwise in the epilogue: frame-aligned tiles, BN = 256 (see Cfg)
     const int px = a.dw_w * a.dw_w;
     if (a.amode != A_PLAIN || a.N % 256 != 0 || px < 1 || px > kHidTileRows || a.M % px != 0 || !a.dwp || a.ldc != a.N ||

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
 // ~16 KB in flight per SM and ran at 1.3 TB/s); then unit = (output pixel, 16-byte channel chunk): nine
 // conflict-free LDS.128, packed bf16x2 FMAs (same arithmetic as the fused kernel's depthwise), one 16 B store.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDwSmemMax = 56 * 1024;
+constexpr int kDwSmemMax = 56 * 1024;       // band budget: four CTAs per SM
+constexpr int kDwSmemLimit = 100 * 1024;    // 160-pixel rows (unfused A/B path only): three input rows need 62 KB
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
@@ -540,8 +541,8 @@ int kernels_init() {
   int e = (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(AttnSmem) + 1024);
   e |= (int)cudaFuncSetAttribute(inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IncSmem) + 1024);
-  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
-  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemMax);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
   return e;
 }
 
@@ -556,7 +557,10 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp
   const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
   // rows per band: the input band (BR*stride + 2 rows of (W+2) pixels x 128 B) must fit the smem budget
   const int row_bytes = (W + 2) * 128;
-  int BR = ((kDwSmemMax - 1024) / row_bytes - 3) / stride + 1;
+  int budget = kDwSmemMax;
+  if ((budget - 1024) / row_bytes < 3) budget = 3 * row_bytes + 1024;   // one output row per band
+  if (budget > kDwSmemLimit) return (int)cudaErrorInvalidValue;
+  int BR = ((budget - 1024) / row_bytes - 3) / stride + 1;
   if (BR < 1) return (int)cudaErrorInvalidValue;
   if (BR > Ho) BR = Ho;
   const int bands = (Ho + BR - 1) / BR;

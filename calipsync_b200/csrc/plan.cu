@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -198,6 +199,8 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
 struct casync_plan {
+  mutable std::mutex mu;            // one forward / stage call at a time: lanes, events, graph cache and chain state are shared
+  int device = 0;                   // the CUDA device the plan was created on (streams, events, graphs live there)
   const uint8_t* dev = nullptr;
   std::vector<int64_t> off;
   IncParams inc;
@@ -809,6 +812,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   CK(kernels_init());
   CK(chain_init());
   casync_plan* p = new casync_plan;
+  cudaGetDevice(&p->device);
   p->dev = reinterpret_cast<const uint8_t*>(dev_blob);
   p->off.assign(offsets, offsets + n_entries);
   const uint8_t* hb = reinterpret_cast<const uint8_t*>(host_blob);
@@ -877,6 +881,11 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
 }
 
 void casync_plan_destroy(casync_plan* plan) {
+  int prev_dev = -1;
+  if (plan) {   // synchronise and release on the plan's device, whatever the caller's current device is
+    cudaGetDevice(&prev_dev);
+    if (prev_dev != plan->device) cudaSetDevice(plan->device); else prev_dev = -1;
+  }
   if (plan && plan->phase_dbg && plan->strip_ir && plan->phase_dbg_ir > 0 && plan->phase_dbg_ir < kNumIr &&
       strip_ir_supported(kIr[plan->phase_dbg_ir].cin, kIr[plan->phase_dbg_ir].cout, kIr[plan->phase_dbg_ir].h_in,
                          kIr[plan->phase_dbg_ir].stride, plan->phase_dbg_ir >= IR_UP && !((plan->phase_dbg_ir - IR_UP) & 1),
@@ -954,6 +963,7 @@ void casync_plan_destroy(casync_plan* plan) {
       if (ev) cudaEventDestroy(ev);
   }
   delete plan;
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
 }
 
 int casync_chunk_frames(const casync_plan* plan) { return plan ? plan->chunk : 0; }
@@ -1031,6 +1041,13 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
   if (flags & CASYNC_F_FP32) return fail(CASYNC_EUNSUP, "fp32 arithmetic path is not implemented");
   if ((uintptr_t)workspace & 255) return fail(CASYNC_EINVAL, "workspace must be 256-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Calls on one plan are serialised (threads that share a Model; ctypes releases the GIL).  The lock covers the host
+  // side only: two forwards enqueued on DIFFERENT streams still share the workspace -- the caller orders them with an
+  // event (calipsync_b200.Model does) or uses one stream.
+  std::lock_guard<std::mutex> guard(plan->mu);
+  int cur_dev = -1;
+  if (cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev != plan->device)
+    return fail(CASYNC_EDEVICE, "plan belongs to device %d but the current device is %d", plan->device, cur_dev);
   if (!plan->use_graphs || plan->use_chain || g_prof) return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
@@ -1170,6 +1187,7 @@ int casync_ir_block(const casync_plan* plan, int ir_index, const void* in, void*
     return fail(CASYNC_EINVAL, "ir index %d not runnable here (0 = inc takes the fp32 NCHW input)", ir_index);
   if (ir_index >= IR_UP && !((ir_index - IR_UP) & 1))
     return fail(CASYNC_EINVAL, "decoder block %d consumes (low, skip): use casync_up_block", ir_index);
+  std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
   chain_begin(plan, w, batch);
   int e = run_ir(plan, ir_index, reinterpret_cast<const bf16*>(in), nullptr, reinterpret_cast<bf16*>(out),
@@ -1181,6 +1199,7 @@ int casync_ir_block(const casync_plan* plan, int ir_index, const void* in, void*
 
 int casync_audio_cnn(const casync_plan* plan, const float* audio, void* out, void* scratch, int batch, void* stream) {
   if (!plan || !audio || !out || !scratch || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
   chain_begin(plan, w, batch);
   int e = run_audio(plan, audio, reinterpret_cast<bf16*>(out), 512, w, batch, reinterpret_cast<cudaStream_t>(stream));
@@ -1193,6 +1212,7 @@ int casync_fusion_attention(const casync_plan* plan, const void* x5, const void*
                             int batch, void* stream) {
   if (!plan || !x5 || !audio || !kx || !scratch || batch <= 0 || batch > plan->chunk)
     return fail(CASYNC_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t rows = (size_t)batch * 100;
@@ -1209,11 +1229,28 @@ int casync_up_block(const casync_plan* plan, int level, const void* low, const v
                     int batch, void* stream) {
   if (!plan || !low || !skip || !out || !scratch || batch <= 0 || batch > plan->chunk || level < 1 || level > 4)
     return fail(CASYNC_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
   const char* tmp[4] = {"t_up1", "t_up2", "t_up3", "t_up4"};
   chain_begin(plan, w, batch);
   int e = run_up(plan, level, reinterpret_cast<const bf16*>(low), reinterpret_cast<const bf16*>(skip), w[tmp[level - 1]],
                  reinterpret_cast<bf16*>(out), w, batch, reinterpret_cast<cudaStream_t>(stream));
+  if (e) return e;
+  CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int casync_up_first(const casync_plan* plan, int level, const void* low, const void* skip, void* out, void* scratch,
+                    int batch, void* stream) {
+  if (!plan || !low || !skip || !out || !scratch || batch <= 0 || batch > plan->chunk || level < 1 || level > 4)
+    return fail(CASYNC_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> guard(plan->mu);
+  Workspace w(scratch, batch);
+  chain_begin(plan, w, batch);
+  const int i0 = IR_UP + 2 * (level - 1);
+  int e = run_ir(plan, i0, reinterpret_cast<const bf16*>(skip), reinterpret_cast<const bf16*>(low),
+                 reinterpret_cast<bf16*>(out), kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch,
+                 reinterpret_cast<cudaStream_t>(stream));
   if (e) return e;
   CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
   return 0;

@@ -13,6 +13,7 @@ CUDA path cannot do raises ``RuntimeError`` (which the reference's callers catch
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 import torch.nn as nn
@@ -92,14 +93,42 @@ class Model(nn.Module):
         self.bn_tx = nn.BatchNorm2d(c[4] * 2)
         self._plan = None          # (handle, device blob, device)
         self._workspace = None
+        self._lock = threading.Lock()   # one forward at a time per Model: plan, lanes and workspace are shared state
+        self._last = None          # (stream id, event) of the last forward: orders forwards issued on different streams
 
     # ---- packed-weight lifecycle --------------------------------------------------------------------------------
     def _invalidate(self):
         plan = self.__dict__.get("_plan")
         if plan is not None:
-            _lib.load().casync_plan_destroy(plan[0])
+            with torch.cuda.device(plan[2]):   # destroy synchronises the plan's own device, not the current one
+                _lib.load().casync_plan_destroy(plan[0])
         self._plan = None
         self._workspace = None
+        self._last = None
+
+    # The plan handle, the workspace and the lock are process-local (ctypes pointers cannot be pickled): copies and
+    # pickles carry the parameters only and rebuild the packed weights lazily, like the reference nn.Module would.
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_plan"] = None
+        d["_workspace"] = None
+        d["_last"] = None
+        d.pop("_lock", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._lock = threading.Lock()
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new._lock = threading.Lock()
+        return new
 
     def _apply(self, fn, *a, **k):           # .to() / .cuda() / .half() ...
         self._invalidate()
@@ -170,14 +199,24 @@ class Model(nn.Module):
 
     def _run(self, x, audio_feat, out, flags):
         device = x.device
-        handle = self._ensure_plan(device)
-        ws = self._ensure_workspace(handle, x.shape[0], device)
         x, audio_feat = x.contiguous(), audio_feat.contiguous()
-        with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
+        # One forward at a time per Model (the reference nn.Module may be called from several threads / streams): the
+        # plan's lanes, events, graph cache and the workspace are shared.  Threads serialise on the lock; a forward
+        # issued on another CUDA stream than the previous one first waits for that one's completion event.
+        with self._lock, torch.cuda.device(device):
+            handle = self._ensure_plan(device)
+            cur = torch.cuda.current_stream(device)
+            last = self._last
+            if last is not None and last[0] != cur.cuda_stream:
+                cur.wait_event(last[1])
+            ws = self._ensure_workspace(handle, x.shape[0], device)
+            ws.record_stream(cur)
             rc = _lib.load().casync_forward(handle, x.data_ptr(), audio_feat.data_ptr(), out.data_ptr(), ws.data_ptr(),
-                                            x.shape[0], flags, ctypes.c_void_p(stream))
-        _lib.check(rc, "casync_forward")
+                                            x.shape[0], flags, ctypes.c_void_p(cur.cuda_stream))
+            _lib.check(rc, "casync_forward")
+            ev = last[1] if last is not None else torch.cuda.Event()
+            ev.record(cur)
+            self._last = (cur.cuda_stream, ev)
         return out
 
     @torch.no_grad()

@@ -127,6 +127,10 @@ CASYNC_API int casync_fusion_attention(const casync_plan *plan, const void *x5, 
 /* Up (module/unet.py:82-97), level 1..4: low [B,h,w,C] + skip [B,2h,2w,C] -> [B,2h,2w,Cout] */
 CASYNC_API int casync_up_block(const casync_plan *plan, int level, const void *low, const void *skip, void *out, void *scratch,
                     int batch, void *stream);
+/* first InvertedResidual of Up only (up<level>.conv.double_conv.0: bilinear x2 + concat + block), for unit tests / ncu:
+   low [B,h,w,C] + skip [B,2h,2w,C] -> [B,2h,2w,Cout0] (module/unet.py:90-96 + :8-40) */
+CASYNC_API int casync_up_first(const casync_plan *plan, int level, const void *low, const void *skip, void *out, void *scratch,
+                    int batch, void *stream);
 
 #ifdef __cplusplus
 }

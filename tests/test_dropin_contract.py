@@ -82,3 +82,25 @@ def test_schema_and_ir_table_are_consistent():
     for d in irs:
         assert d["name"] + ".conv.0.weight" in names
     assert calipsync_b200.shard_sizes(1500, 8) == [188] * 7 + [184]
+
+
+def test_copy_and_pickle_like_the_reference_module():
+    """copy.deepcopy / torch.save(model) / pickle of the whole module work as for the reference nn.Module (EMA copies,
+    whole-module checkpoints): the process-local plan handle and workspace are dropped and rebuilt lazily."""
+    import copy
+    import io
+    import pickle
+    m = Model(6, "hubert").eval()
+    m._plan = (ctypes.c_void_p(0), torch.zeros(1), torch.device("cpu"))   # what a forward leaves behind (opaque handle)
+    try:
+        for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+            assert clone._plan is None and clone._workspace is None
+            assert list(clone.state_dict().keys()) == list(m.state_dict().keys())
+            assert all(torch.equal(a, b) for a, b in zip(clone.state_dict().values(), m.state_dict().values()))
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        again = torch.load(buf, weights_only=False)
+        assert again._plan is None and not again.training
+    finally:
+        m._plan = None

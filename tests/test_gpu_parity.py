@@ -53,9 +53,11 @@ def test_forward_matches_golden_and_oracle_stages(regime):
             assert O.psnr_db(out[i], tgt[i]) >= MIN_PSNR
 
 
-def test_config2_batch64_tolerance():
-    """BASELINE config 2: batch 64, bf16 on one B200 vs the fp32 reference arithmetic (oracle)."""
-    model, sd = make_model("R1", seed=1)
+@pytest.mark.parametrize("regime", ["R0", "R1"])
+def test_config2_batch64_tolerance(regime):
+    """BASELINE config 2: batch 64, bf16 on one B200 vs the fp32 reference arithmetic (oracle), default-init (R0) and
+    perturbed (R1) weights."""
+    model, sd = make_model(regime, seed=1)
     x, a = O.make_inputs(64, 11)
     out = model(x.cuda(), a.cuda()).cpu()
     ref = torch.cat([O.forward(sd, x[i:i + 16], a[i:i + 16]) for i in range(0, 64, 16)])
@@ -96,8 +98,8 @@ def test_uint8_hwc_epilogue_truncates_like_the_caller():
     u = model.forward_uint8(x.cuda(), a.cuda()).cpu()
     assert u.shape == (3, 160, 160, 3) and u.dtype == torch.uint8
     expect = np.array(f.numpy().transpose(0, 2, 3, 1) * 255, dtype=np.uint8)
-    diff = np.abs(u.numpy().astype(np.int32) - expect.astype(np.int32))
-    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3      # fp32 product rounding at integer boundaries only
+    # byte work: the kernel truncates the very fp32 product the caller computes -> exact, not "close"
+    assert np.array_equal(u.numpy(), expect)
 
 
 def test_three_argument_convenience_and_input_preservation():
@@ -140,6 +142,51 @@ def test_called_from_worker_thread_on_side_stream():
     t.start()
     t.join()
     assert torch.equal(got["out"], want)
+
+
+def test_two_threads_sharing_one_model_serialise():
+    """Two Python threads calling ONE Model on their own streams (ctypes releases the GIL): calls serialise on the
+    model's lock and on a completion event, so both get the single-threaded result (the reference nn.Module is safe
+    under this use; plan, lanes and workspace are shared state here)."""
+    import threading
+    model, _ = make_model("R1", seed=6)
+    ins = [O.make_inputs(24 + i, 40 + i) for i in range(2)]         # >= 24 frames: two-lane split, plan-owned streams
+    want = [model(x.cuda(), a.cuda()).clone() for x, a in ins]
+    got = [[None] * 6, [None] * 6]
+    errs = []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            xg, ag = ins[i][0].cuda(), ins[i][1].cuda()
+            torch.cuda.synchronize()
+            with torch.cuda.stream(s):
+                for r in range(6):
+                    got[i][r] = model(xg, ag)
+            s.synchronize()
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        for r in range(6):
+            assert torch.equal(got[i][r], want[i]), (i, r)
+
+
+def test_unfused_switch_runs_every_block_through_the_gemm_path(monkeypatch):
+    """CASYNC_NO_FUSED_IR=1 (INTEGRATION.md A/B switch): every InvertedResidual as pw1 GEMM + depthwise + pw2 GEMM,
+    including the 32-channel blocks whose K is half a 64-channel k-block.  Same tolerance as the default path."""
+    monkeypatch.setenv("CASYNC_NO_FUSED_IR", "1")
+    model, sd = make_model("R1", seed=7)
+    x, a = O.make_inputs(3, 13)
+    out = model(x.cuda(), a.cuda()).cpu()
+    ref = O.forward(sd, x, a)
+    assert O.max_abs_255(out, ref) <= MAX_ABS_255 and O.psnr_db(out, ref) >= MIN_PSNR
 
 
 def test_host_pipeline_equals_direct_forward():

@@ -34,21 +34,68 @@ def nchw(t, b, h, c):
     return t.float().cpu().reshape(b, h, h, c).permute(0, 3, 1, 2)
 
 
-@pytest.mark.parametrize("idx", [1, 2, 3, 4, 7, 8, 9, 11, 13, 14, 17, 19, 21, 23, 25])
-def test_inverted_residual_block(ctx, idx):
+_IR_STANDALONE = [i for i in range(1, 26) if i not in (18, 20, 22, 24)]   # 18..24 even: decoder blocks, test_up_first
+
+
+@pytest.fixture(scope="module")
+def ctx64(ctx):
+    """Same model, scratch sized for BASELINE configs[1]'s batch (64 frames)."""
+    scratch = torch.empty(ctx["lib"].casync_stage_scratch_bytes(ctx["plan"], 64), dtype=torch.uint8, device="cuda")
+    return dict(ctx, scratch=scratch)
+
+
+def _run_ir(c, idx, batch):
     d = _lib.ir_table()[idx]
     g = torch.Generator().manual_seed(idx)
-    xin = (torch.randn(2, d["cin"], d["h_in"], d["h_in"], generator=g) * 0.3).bfloat16().float()
-    ref = O.inverted_residual(ctx["sd"], d["name"], xin, d["stride"], bool(d["residual"]))
+    xin = (torch.randn(batch, d["cin"], d["h_in"], d["h_in"], generator=g) * 0.3).bfloat16().float()
+    ref = O.inverted_residual(c["sd"], d["name"], xin, d["stride"], bool(d["residual"]))
     ho = d["h_in"] // d["stride"]
-    out = torch.empty(2 * ho * ho, d["cout"], dtype=torch.bfloat16, device="cuda")
+    out = torch.empty(batch * ho * ho, d["cout"], dtype=torch.bfloat16, device="cuda")
     xin_d = nhwc(xin)          # keep device inputs alive while the kernels run
-    rc = ctx["lib"].casync_ir_block(ctx["plan"], idx, xin_d.data_ptr(), out.data_ptr(), ctx["scratch"].data_ptr(), 2,
-                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = c["lib"].casync_ir_block(c["plan"], idx, xin_d.data_ptr(), out.data_ptr(), c["scratch"].data_ptr(), batch,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "casync_ir_block")
     torch.cuda.synchronize()
-    err = O.rel_l2(nchw(out, 2, ho, d["cout"]), ref)
-    assert err < TOL, (d["name"], err)
+    err = O.rel_l2(nchw(out, batch, ho, d["cout"]), ref)
+    assert err < TOL, (d["name"], batch, err)
+
+
+@pytest.mark.parametrize("idx", _IR_STANDALONE)
+def test_inverted_residual_block(ctx, idx):
+    """Every InvertedResidual instance that takes one input tensor (21 of 26; inc is covered by stage x1, the four
+    decoder-first blocks by test_up_first), at batch 2."""
+    _run_ir(ctx, idx, 2)
+
+
+@pytest.mark.parametrize("idx", _IR_STANDALONE)
+def test_inverted_residual_block_batch64(ctx64, idx):
+    """The same blocks at BASELINE configs[1]'s batch: every CTA of the persistent kernels has several tiles / strips,
+    frames straddle row tiles (M = 64 * H * W is not a multiple of 128 at 10x10)."""
+    _run_ir(ctx64, idx, 64)
+
+
+@pytest.mark.parametrize("level,batch", [(1, 2), (2, 2), (3, 2), (4, 2), (3, 64), (4, 64)])
+def test_up_first(ctx, ctx64, level, batch):
+    """up<level>.conv.double_conv.0 alone (IR indices 18, 20, 22, 24): bilinear x2 (align_corners) + concat + block.
+    Levels 3 and 4 (the two hottest kernels of the step) also at batch 64."""
+    import torch.nn.functional as F
+    c = ctx64 if batch > 2 else ctx
+    idx = 18 + 2 * (level - 1)
+    d = _lib.ir_table()[idx]
+    h = d["h_in"]
+    g = torch.Generator().manual_seed(100 + level)
+    low = (torch.randn(batch, d["cin"] // 2, h // 2, h // 2, generator=g) * 0.3).bfloat16().float()
+    skip = (torch.randn(batch, d["cin"] // 2, h, h, generator=g) * 0.3).bfloat16().float()
+    cat = torch.cat([F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True), skip], dim=1)
+    ref = O.inverted_residual(c["sd"], d["name"], cat, 1, False)
+    out = torch.empty(batch * h * h, d["cout"], dtype=torch.bfloat16, device="cuda")
+    low_d, skip_d = nhwc(low), nhwc(skip)
+    rc = c["lib"].casync_up_first(c["plan"], level, low_d.data_ptr(), skip_d.data_ptr(), out.data_ptr(),
+                                  c["scratch"].data_ptr(), batch, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "casync_up_first")
+    torch.cuda.synchronize()
+    err = O.rel_l2(nchw(out, batch, h, d["cout"]), ref)
+    assert err < 2e-2, (d["name"], batch, err)
 
 
 def test_audio_cnn(ctx):
