@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "unet_frames_per_sec_160x160_bf16", "frames/s"
 FLOP_PER_FRAME = 7.9017e9          # 2 x 3.95086 GMAC
+STAGEWISE_US_PER_FRAME = 7.11      # sum over stages of max(t_TC, t_HBM) on the measured peaks
 L2_BYTES = 126e6
 
 
@@ -313,6 +314,49 @@ def main():
     fps_e2e_fr = world * B * args.steps / (ms_fr / 1e3)
     host_sets = keep
 
+    # ---- BASELINE config 3: a 1500-frame clip, strong-scaled (contiguous frame shards), ordered gather INSIDE the timed
+    # region: every batch of uint8 frames goes to rank 0 on a side stream while the next batch is computed
+    from calipsync_b200 import frame_shard, synthesize_clip
+    clip_n = 1500
+    clo, chi = frame_shard(clip_n, rank, world)
+    gclip = torch.Generator(device=device).manual_seed(4242)            # same features on every rank (replicated)
+    clip_feats = torch.randn(clip_n, 2, 1024, device=device, generator=gclip)
+    clip_crops = torch.randint(0, 256, (chi - clo, 160, 160, 3), dtype=torch.uint8, device=device,
+                               generator=torch.Generator(device=device).manual_seed(5000 + rank))
+    clip = {}
+    for cb in (64, 256):
+        for _ in range(2):                                              # warm-up: communicator, graphs, allocator
+            synthesize_clip(net, clip_crops, clip_feats, clip_n, cb)
+        barrier()
+        reps = 3
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            full = synthesize_clip(net, clip_crops, clip_feats, clip_n, cb)
+        ev1.record()
+        barrier()
+        m = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        clip[str(cb)] = {"ms_per_clip": float(m.item()) / reps, "frames_per_s": clip_n * reps / (float(m.item()) / 1e3)}
+        if rank == 0:
+            assert full.shape == (clip_n, 160, 160, 3)
+    del clip_crops, clip_feats, full
+
+    # ---- BASELINE config 5: batch sweep (device-resident inputs, every rank its own batch, max-over-ranks device time)
+    sweep = {}
+    if not args.no_sweep:
+        for b in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+            try:
+                xs = [synth_inputs(b, device, 7 + i) for i in range(2 if b >= 128 else 8)]
+                n = max(3, min(40, 8192 // b))
+                m, _, _ = timed(lambda i: net(*xs[i % len(xs)]), n, 3, len(xs))
+                sweep[str(b)] = round(world * b * n / (m / 1e3), 1)
+                del xs
+            except Exception as e:      # report, never hide
+                sweep[str(b)] = "error: %s" % e
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,6 +380,9 @@ def main():
         stages.append({"kernel": name, "ms": round(v["ms"], 4), "share": round(v["ms"] / total_ms, 4), "bound": bound,
                        "gbs": round(gbs, 1), "tflops": round(tfs, 2),
                        "frac": round(tfs / tc_peak if bound == "tensor" else gbs / hbm_peak, 4)})
+    # whole step against the per-stage roofline: sum of max(t_TC, t_HBM) over the launches / measured time
+    sus = pk.get("bf16_tflops_sustained", tc_peak)
+    budget_ms = sum(max(v["flops"] / (sus * 1e12), v["bytes"] / (hbm_peak * 1e9)) for v in acc.values()) * 1e3
     top = stages[0]
     traffic = None
     try:
@@ -348,21 +395,15 @@ def main():
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (burst)" if pk_kind == "measured" else "fallback (B200_PROFILING.md)",
                 "share_of_step": top["share"],
-                "whole_step": {"tflops": round(fps / world * FLOP_PER_FRAME / 1e12, 1),
+                "whole_step": {"stagewise_frac": round(STAGEWISE_US_PER_FRAME * 1e-3 * B / (ms / args.steps), 4),
+                               "stagewise_budget_ms": round(STAGEWISE_US_PER_FRAME * 1e-3 * B, 4),
+                               "launchwise_frac": round(budget_ms / (ms / args.steps), 4),
+                               "launchwise_note": "per-launch algorithmic bytes/flops incl. the hidden tensors of the "
+                                                  "blocks that are not fused; stagewise = SURVEY 8(d) budget (one "
+                                                  "kernel per block, block input + output only)",
+                               "tflops": round(fps / world * FLOP_PER_FRAME / 1e12, 1),
                                "frac_of_sustained_bf16": round(fps / world * FLOP_PER_FRAME / 1e12 /
                                                                pk.get("bf16_tflops_sustained", tc_peak), 4)}}
-
-    sweep = {}
-    if not args.no_sweep and world == 1:
-        for b in (1, 8, 256, 1024):
-            try:
-                xs = [synth_inputs(b, device, 7 + i) for i in range(2 if b >= 256 else 8)]
-                n = max(3, min(40, 4096 // b))
-                m, _, _ = timed(lambda i: net(*xs[i % len(xs)]), n, 3, len(xs))
-                sweep[str(b)] = round(b * n / (m / 1e3), 1)
-                del xs
-            except Exception as e:      # report, never hide
-                sweep[str(b)] = "error: %s" % e
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -371,6 +412,36 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle port (torch fp32 CPU): batch 8 x 8 iters (median); batch 1: %.2f frames/s; host cpus %d"
                          % (v1, os.cpu_count())}
+
+    gpu_ref = None
+    if not args.no_cpu_baseline and world == 1:
+        # the reference's own deployment is eager PyTorch on the GPU: time the oracle port there too (fp32 and bf16
+        # autocast), same batch.  Checker code, not the product path.
+        try:
+            from oracle import casync_oracle as O
+            sd_g = {k: v.to(device) for k, v in net.state_dict().items()}
+            xg, ag = sets[0]
+
+            def t_ref(n, autocast):
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    for _ in range(2):
+                        O.forward(sd_g, xg, ag)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(n):
+                        O.forward(sd_g, xg, ag)
+                    e1.record()
+                    torch.cuda.synchronize()
+                return B * n / (e0.elapsed_time(e1) / 1e3)
+
+            gpu_ref = {"what": "oracle port of module/unet.py forward as eager PyTorch on the same B200 (cuDNN/cuBLAS), batch %d" % B,
+                       "fp32_frames_per_s": round(t_ref(5, False), 1), "bf16_autocast_frames_per_s": round(t_ref(5, True), 1)}
+            gpu_ref["speedup_vs_fp32_eager"] = round(fps / gpu_ref["fp32_frames_per_s"], 2)
+            gpu_ref["speedup_vs_bf16_autocast_eager"] = round(fps / gpu_ref["bf16_autocast_frames_per_s"], 2)
+            del sd_g
+        except Exception as e:          # noqa: BLE001
+            gpu_ref = {"error": str(e)}
 
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -389,9 +460,14 @@ def main():
                 "uint8_out_value": fps_e2e_u8, "uint8_out_d2h_bytes_per_step": B * 160 * 160 * 3,
                 "frames_api_value": fps_e2e_fr, "frames_api_h2d_bytes_per_step": B * (160 * 160 * 3 + 4),
                 "frames_api": "HostPipeline(frames=True): uint8 crops + frame indices in, uint8 frames out; input "
-                              "assembly (infer_api.py:99-145, 238-245) runs on the device"},
+                              "assembly (infer_api.py:99-145, 238-245) runs on the device",
+                "clip_gathered_value": clip["64"]["frames_per_s"], "clip_gathered": clip,
+                "clip": "BASELINE configs[2]: 1500-frame clip, contiguous frame shards over %d GPU(s), forward_frames in "
+                        "batches of 64 / 256, every batch gathered in order to rank 0 on a side stream (inside the timed "
+                        "region, max over ranks); strong scaling" % world},
         "gpu_launches": net.launches_per_forward(B) * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu, "stages": stages[:12], "batch_sweep_frames_per_s": sweep,
+        "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_reference": gpu_ref, "stages": stages[:12],
+        "batch_sweep_frames_per_s": sweep,
     }
     print(json.dumps(line))
     if world > 1:

@@ -6,7 +6,7 @@ PyTorch fallback: without the built extension, or on a device that is not comput
 forward raises.
 """
 from .unet import Model  # noqa: F401
-from .sharding import frame_shard, shard_sizes  # noqa: F401
+from .sharding import frame_shard, gather_chunked, shard_sizes, synthesize_clip  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["Model", "HostPipeline", "frame_shard", "shard_sizes"]
+__all__ = ["Model", "HostPipeline", "frame_shard", "shard_sizes", "gather_chunked", "synthesize_clip"]
