@@ -102,6 +102,26 @@ def test_uint8_hwc_epilogue_truncates_like_the_caller():
     assert np.array_equal(u.numpy(), expect)
 
 
+def test_predictions_for_the_unmodified_callers_batch():
+    """tests/golden/caller_batch.npz was recorded from the reference's own FrameSynthesizer.process_batch (reference
+    Model, CPU): the crops it cut, the HuBERT windows it built and the uint8 frames it pasted back.  Fed with exactly
+    those inputs the CUDA path must give the caller the same bytes within 2/255 -- through forward() + the caller's own
+    `* 255 -> uint8` and through the uint8 epilogue."""
+    gold = np.load(os.path.join(GOLD, "caller_batch.npz"))
+    model, _ = make_model("R1", seed=5)
+    x = O.assemble_x(gold["crops"]).cuda()
+    a = torch.from_numpy(gold["audio"]).cuda()
+    pred = model(x, a)
+    got = np.stack([np.array(pred[i].cpu().numpy().transpose(1, 2, 0) * 255, dtype=np.uint8) for i in range(len(pred))])
+    diff = np.abs(got.astype(np.int32) - gold["pred_u8"].astype(np.int32))
+    print("\n[caller batch] max |byte diff| = %d, differing bytes %.2f %%" % (diff.max(), 100 * (diff != 0).mean()))
+    assert diff.max() <= 2
+    assert np.array_equal(model.forward_uint8(x, a).cpu().numpy(), got)
+    u = model.forward_frames(torch.from_numpy(gold["crops"]).cuda(), torch.zeros(1, 2, 1024).cuda(),
+                             torch.zeros(len(pred), dtype=torch.int32).cuda())     # shape / dtype contract of the frames API
+    assert u.shape == got.shape and u.dtype == torch.uint8
+
+
 def test_three_argument_convenience_and_input_preservation():
     model, _ = make_model("R0")
     x, a = O.make_inputs(2, 5)
