@@ -8,5 +8,6 @@ forward raises.
 from .unet import Model  # noqa: F401
 from .sharding import frame_shard, gather_chunked, shard_sizes, synthesize_clip  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
+from .blend import blend_paste  # noqa: F401
 
-__all__ = ["Model", "HostPipeline", "frame_shard", "shard_sizes", "gather_chunked", "synthesize_clip"]
+__all__ = ["Model", "HostPipeline", "frame_shard", "shard_sizes", "gather_chunked", "synthesize_clip", "blend_paste"]

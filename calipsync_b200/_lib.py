@@ -33,6 +33,7 @@ SYMBOLS = [
     ("casync_fusion_attention", _I, [_P, _P, _P, _P, _P, _I, _P]),
     ("casync_up_block", _I, [_P, _I, _P, _P, _P, _P, _I, _P]),
     ("casync_up_first", _I, [_P, _I, _P, _P, _P, _P, _I, _P]),
+    ("casync_blend_paste", _I, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _P]),
 ]
 
 

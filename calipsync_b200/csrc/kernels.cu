@@ -572,6 +572,41 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp
   return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR);
 }
 
+// ---- paste-back blend -------------------------------------------------------------------------------------------------
+// One thread per region pixel.  numpy evaluates (crop * m) + (img * (1.0 - m)) in float64 with one rounding per
+// operation and casts to uint8 by truncation: __dmul_rn / __dadd_rn / __dsub_rn keep the compiler from contracting the
+// expression into FMAs, which would change the last bit of some products.
+__global__ void blend_paste_kernel(uint8_t* frames, int H, int W, const uint8_t* crops, int ldc, const uint8_t* face,
+                                   const float* soft, const int4* rects, int batch) {
+  const int b = blockIdx.y;
+  const int4 r = rects[b];   // ymin, ymax, xmin, xmax
+  const int h = r.y - r.x, w = r.w - r.z;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h <= 0 || w <= 0 || i >= h * w) return;
+  const int y = i / w, x = i - y * w;
+  if (y >= ldc || x >= ldc || r.x + y < 0 || r.x + y >= H || r.z + x < 0 || r.z + x >= W) return;
+  const size_t mi = ((size_t)b * ldc + y) * ldc + x;
+  double m = (double)face[mi] / 255.0;
+  if (soft) {
+    const float inv = 1.0f - soft[mi];          // float32, as numpy keeps the mask file's dtype
+    m = __dmul_rn(m, (double)(1.0f - inv));
+  }
+  const double om = __dsub_rn(1.0, m);
+  uint8_t* dst = frames + (((size_t)b * H + r.x + y) * W + r.z + x) * 3;
+  const uint8_t* src = crops + mi * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    dst[c] = (uint8_t)__dadd_rn(__dmul_rn((double)src[c], m), __dmul_rn((double)dst[c], om));
+}
+
+int launch_blend_paste(uint8_t* frames, int H, int W, const uint8_t* crops, int ldc, const uint8_t* face, const float* soft,
+                       const int* rects, int batch, cudaStream_t st) {
+  if (batch <= 0 || ldc <= 0 || H <= 0 || W <= 0 || ((uintptr_t)rects & 15)) return (int)cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((ldc * ldc + 255) / 256), (unsigned)batch);
+  blend_paste_kernel<<<grid, 256, 0, st>>>(frames, H, W, crops, ldc, face, soft, reinterpret_cast<const int4*>(rects), batch);
+  return (int)cudaGetLastError();
+}
+
 int launch_prepare_inputs(const uint8_t* crops, const float* feats, int T, const int* frame_idx, float* x, float* audio,
                           int batch, cudaStream_t st) {
   const long npix = (long)batch * 25600, n4 = (long)batch * 8192;

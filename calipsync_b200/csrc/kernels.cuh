@@ -45,6 +45,9 @@ int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfl
                 cudaStream_t st);
 // sigmoid(outc_bn(outc(x)))  ->  fp32 NCHW [B,3,160,160] or uint8 HWC floor(p*255)
 int launch_outc(const __nv_bfloat16* x, void* out, const OutcParams& w, int batch, int u8_hwc, cudaStream_t st);
+// paste-back blend (infer_api.py:333-346): frames[region] = uint8(crop * m + frames[region] * (1 - m)) in float64
+int launch_blend_paste(uint8_t* frames, int H, int W, const uint8_t* crops, int ldc, const uint8_t* face, const float* soft,
+                       const int* rects, int batch, cudaStream_t st);
 int kernels_init();
 
 }  // namespace casync

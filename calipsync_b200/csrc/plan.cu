@@ -1149,6 +1149,15 @@ int casync_prepare_inputs(const uint8_t* crops_hwc, const float* feats, int n_fe
   return 0;
 }
 
+int casync_blend_paste(uint8_t* frames, int H, int W, const uint8_t* crops, int ldc, const uint8_t* face_mask,
+                       const float* soft_mask, const int32_t* rects, int batch, void* stream) {
+  if (!frames || !crops || !face_mask || !rects) return fail(CASYNC_EINVAL, "null argument");
+  if (batch <= 0 || H <= 0 || W <= 0 || ldc <= 0) return fail(CASYNC_EINVAL, "batch, image and crop sizes must be positive");
+  if ((uintptr_t)rects & 15) return fail(CASYNC_EINVAL, "rects must be 16-byte aligned");
+  CK(launch_blend_paste(frames, H, W, crops, ldc, face_mask, soft_mask, rects, batch, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int casync_stage_view(const casync_plan* plan, int batch, const char* name, size_t* offset, int64_t* rows,
                       int64_t* cols, int64_t* ld) {
   if (!plan || !name || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "stage views need batch <= chunk");

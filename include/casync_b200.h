@@ -85,6 +85,19 @@ CASYNC_API int casync_forward(const casync_plan *plan, const float *x_nchw, cons
 CASYNC_API int casync_prepare_inputs(const uint8_t *crops_hwc, const float *feats, int n_feat_frames,
                                      const int32_t *frame_idx, float *x_nchw, float *audio, int batch, void *stream);
 
+/* Paste-back blend of the caller on the device (infer_api.py:333-346):
+ *   frames[b][ymin+y][xmin+x][c] = uint8( crop * m + frames * (1 - m) ),  m = face_mask/255 (* soft mask)
+ * in float64 with separate multiply / add roundings and truncation -- exactly what numpy computes for
+ * `(crop_img * mask) + (img[ymin:ymax, xmin:xmax] * (1.0 - mask))` assigned into the uint8 image.
+ *   frames     uint8 [batch, H, W, 3], updated in place
+ *   crops      uint8 [batch, ldc, ldc, 3]: the re-sized crop with the prediction pasted in (rows/cols >= the region's
+ *              size are ignored).  The caller's cv2.resize stays where it is: its rounding is OpenCV-build dependent.
+ *   face_mask  uint8 [batch, ldc, ldc]: the dilated face polygon (0 / 255 after fillPoly + dilate + bitwise_and)
+ *   soft_mask  fp32 [batch, ldc, ldc] or NULL: the optional per-frame mask file, already re-sized (infer_api.py:336-343)
+ *   rects      int32 [batch, 4] = (ymin, ymax, xmin, xmax) of every frame's region, on the device */
+CASYNC_API int casync_blend_paste(uint8_t *frames, int H, int W, const uint8_t *crops, int ldc, const uint8_t *face_mask,
+                                  const float *soft_mask, const int32_t *rects, int batch, void *stream);
+
 /* Same as casync_forward, but records one CUDA event after every kernel launch, SYNCHRONISES the stream and
  * returns per-launch device time with the launch's algorithmic FLOPs and activation bytes (weights excluded).
  * Profiling aid for bench.py's roofline line; not for the timed throughput run. */

@@ -191,6 +191,23 @@ def assemble_x(crops_u8):
     return torch.from_numpy(np.stack(out))
 
 
+def blend_paste(img, crop_resized, face_mask_u8, rect, soft_mask=None):
+    """The paste-back blend of FrameSynthesizer.process_batch, image_infer_v1/tools/frame_synthesizer/infer_api.py:313-346,
+    for one frame (numpy, float64 like the reference): img uint8 [H,W,3] (a modified copy is returned), crop_resized
+    uint8 [h,w,3] = the re-sized crop with the prediction pasted in, face_mask_u8 uint8 [h,w] = the dilated polygon
+    (`final_face_mask`), rect = (ymin, ymax, xmin, xmax), soft_mask float32 [h,w] = the re-sized per-frame mask or None."""
+    import numpy as np
+    ymin, ymax, xmin, xmax = rect
+    m3 = np.repeat((face_mask_u8 / 255.0)[..., np.newaxis], 3, axis=2)                      # :313-314
+    if soft_mask is not None:
+        s3 = np.repeat(soft_mask[..., np.newaxis], 3, axis=2)                               # :336
+        inverted = 1.0 - s3                                                                 # :339
+        m3 = m3 * (1.0 - inverted)                                                          # :342
+    out = img.copy()
+    out[ymin:ymax, xmin:xmax] = (crop_resized * m3) + (img[ymin:ymax, xmin:xmax] * (1.0 - m3))   # :345 / :348, :350
+    return out
+
+
 def _bn(sd, p, x):
     """eval-mode BatchNorm (running statistics), eps=1e-5."""
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],

@@ -57,3 +57,41 @@ def test_drop_in_class_goes_through_the_callers_constructor_and_error_path():
         images, hub, results, calls = g.run_caller(calipsync_b200.Model, "cpu", root, feats, ckpt)
     assert calls == []                                                      # the forward raised before returning
     assert len(results) == len(images) and all(np.array_equal(r, i) for r, i in zip(results, images))
+
+
+def test_oracle_blend_is_the_callers_blend(monkeypatch):
+    """oracle.blend_paste against the reference's own paste-back: cv2.resize / cv2.bitwise_and are wrapped (recording
+    their results while the UNMODIFIED process_batch runs), which yields every frame's re-sized crop and final face mask;
+    the oracle's blend of those must reproduce the frames the caller returned, bit for bit."""
+    import cv2
+    g = _gen()
+    from image_infer_v1.models.unet import Model as RefModel
+    rec = {"resize": [], "and": []}
+    real_resize, real_and = cv2.resize, cv2.bitwise_and
+
+    def resize(src, dsize, *a, **k):
+        out = real_resize(src, dsize, *a, **k)
+        rec["resize"].append((tuple(dsize), out.copy()))
+        return out
+
+    def bitwise_and(a, b, *r, **k):
+        out = real_and(a, b, *r, **k)
+        rec["and"].append(out.copy())
+        return out
+
+    monkeypatch.setattr(cv2, "resize", resize)
+    monkeypatch.setattr(cv2, "bitwise_and", bitwise_and)
+    with tempfile.TemporaryDirectory() as root:
+        feats = g.build_scene(root)
+        ckpt = os.path.join(root, "unet.pth")
+        torch.save(O.make_state_dict(5, "R1"), ckpt)
+        images, hub, results, calls = g.run_caller(RefModel, "cpu", root, feats, ckpt)
+        lms = [np.loadtxt(os.path.join(root, "positions", "%06d.txt" % i)) for i in range(g.N_FRAMES)]
+    n = g.N_FRAMES
+    assert len(rec["and"]) == n and len(rec["resize"]) == 2 * n        # per frame: crop -> 168x168, then back to (w, w)
+    back = [r for r in rec["resize"] if r[0] != (168, 168)]
+    for i in range(n):
+        xmin, ymin, xmax = int(lms[i][1][0]), int(lms[i][52][1]), int(lms[i][31][0])      # crop box (infer_api.py:206-209)
+        rect = (ymin, ymin + (xmax - xmin), xmin, xmax)
+        got = O.blend_paste(images[i], back[i][1], rec["and"][i], rect)
+        assert np.array_equal(got, results[i]), i

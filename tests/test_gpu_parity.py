@@ -122,6 +122,30 @@ def test_predictions_for_the_unmodified_callers_batch():
     assert u.shape == got.shape and u.dtype == torch.uint8
 
 
+@pytest.mark.parametrize("soft", [False, True])
+def test_device_blend_is_bit_exact_with_numpy(soft):
+    """casync_blend_paste against the oracle's restatement of the caller's float64 blend: byte
+    work, so every frame must match exactly -- ragged regions of different sizes per frame, hard 0/255 polygon masks,
+    and the optional soft per-frame mask."""
+    from calipsync_b200 import blend_paste
+    rs = np.random.RandomState(17)
+    b, h, w, ldc = 5, 300, 280, 200
+    frames = rs.randint(0, 256, size=(b, h, w, 3), dtype=np.uint8)
+    crops = rs.randint(0, 256, size=(b, ldc, ldc, 3), dtype=np.uint8)
+    face = (rs.rand(b, ldc, ldc) > 0.4).astype(np.uint8) * 255
+    face[0, :, :7] = 128                                                  # not only 0 / 255: m = 128/255
+    softm = rs.rand(b, ldc, ldc).astype(np.float32) if soft else None
+    rects = np.array([[10, 10 + 200, 5, 5 + 200], [0, 150, 0, 150], [100, 300, 80, 280], [37, 38, 11, 12],
+                      [50, 50 + 173, 60, 60 + 173]], dtype=np.int32)
+    want = np.stack([O.blend_paste(frames[i], crops[i, : rects[i, 1] - rects[i, 0], : rects[i, 3] - rects[i, 2]],
+                                   face[i, : rects[i, 1] - rects[i, 0], : rects[i, 3] - rects[i, 2]], tuple(rects[i]),
+                                   None if softm is None else softm[i, : rects[i, 1] - rects[i, 0], : rects[i, 3] - rects[i, 2]])
+                     for i in range(b)])
+    got = blend_paste(torch.from_numpy(frames.copy()).cuda(), torch.from_numpy(crops).cuda(), torch.from_numpy(face).cuda(),
+                      torch.from_numpy(rects).cuda(), None if softm is None else torch.from_numpy(softm).cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 def test_three_argument_convenience_and_input_preservation():
     model, _ = make_model("R0")
     x, a = O.make_inputs(2, 5)
