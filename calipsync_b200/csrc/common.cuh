@@ -101,7 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 template <int NS>
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
-    asm volatile("nanosleep.u32 %0;" ::"n"(NS));
+    if (NS > 0) asm volatile("nanosleep.u32 %0;" ::"n"(NS));
   }
 }
 

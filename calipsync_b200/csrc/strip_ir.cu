@@ -94,6 +94,9 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 #ifndef STRIP_EXP
 #define STRIP_EXP 0   // developer timing experiments (wrong results): 1 no dw FMAs, 2 no drain math, 4 no bilinear, 8 no epilogue stores
 #endif
+#ifndef STRIP_PUBLISH_TILE_ONLY
+#define STRIP_PUBLISH_TILE_ONLY 0
+#endif
 #ifndef STRIP_DBG
 #define STRIP_DBG 0   // 1: per-role cycle counters (CASYNC_PHASE_DBG=<ir index>)
 #endif
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
           const int v = V0 + acq_k * RPT, bs = v / H, hy = v - bs * H;
           ga = bs * HP + hy - G0;
         }
-        int g = hr - 2;
+        int g = (STRIP_EXP & 32) ? ntop : hr - 2;   // (experiment: ignore the hidden ring's fill level)
         g = g < ga ? g : ga;
         g = g < ntop ? g : ntop;
         if (g > go_pub) {
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
       const int ht = 2 * t + (lg >> 1);   // this warp's half-tile (64 positions): the ring's credit granularity
       mbar_wait_sleep<kSleepNs>(bar(B_D1FULL + b), (t >> 1) & 1);
       T(9);
-      if (ht >= NH) mbar_wait_sleep<kSleepNs>(bar(B_HIDFREE + ht % NH), ((ht / NH) & 1) ^ 1);
+      if (ht >= NH && !(STRIP_EXP & 32)) mbar_wait_sleep<kSleepNs>(bar(B_HIDFREE + ht % NH), ((ht / NH) & 1) ^ 1);
       T(10);
       const bool inside = sm.at<uint8_t>(sMETA + (t & 3) * 128 + row) != 0;
       tc_fence_after();
@@ -410,8 +413,12 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
       const uint32_t hid = sHID + (uint32_t)(q % kRing) * PB;
       const uint32_t h7 = hx & 7;
       const uint32_t tsrc = tmem + b * CH + hw * NCOL + ((uint32_t)(lg * 32) << 16);
+      if (STRIP_EXP & 128) {
+        tc_fence_before();
+        mbar_arrive(bar(B_D1FREE + b));
+      }
 #pragma unroll
-      for (int cc = 0; cc < NCOL; cc += 32) {
+      for (int cc = 0; cc < ((STRIP_EXP & 128) ? 0 : NCOL); cc += 32) {
         uint32_t acc[32];
         tmem_ld32(tsrc + cc, acc);
         tmem_ld_wait32(acc);
@@ -522,9 +529,17 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
         T(15);
         if (jt >= go) wait_go(jt);
         T(13);
-        load_row(bot);
+        if (!(STRIP_EXP & 64)) load_row(bot);
         bool tile_end = false;
-        if (hy < H) {
+        if ((STRIP_EXP & 64) && hy < H) {
+          arow += SW * 128;
+          if (++rcnt == RPT) {
+            rcnt = 0;
+            aslot ^= (uint32_t)kTileB;
+            arow = aslot;
+            tile_end = true;
+          }
+        } else if (hy < H) {
           __nv_bfloat162 a[NC][2];
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
@@ -569,6 +584,13 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
         // progress: a relaxed store is enough for the ring (the row's loads have been consumed by the FMAs above, in
         // order); the row that completes an A2 tile publishes with fence.proxy.async + release so that the agent's
         // A2FULL arrival orders the stores before the tcgen05.mma reads
+#if STRIP_PUBLISH_TILE_ONLY
+        if (tile_end || jt == ntop || hy == 0) {   // (hy == 0: a strip's last halo rows are done -- frees its ring space)
+          __syncwarp();
+          fence_proxy_async();
+          if (lane == 0) st_release_s32(done_addr, (uint32_t)jt);
+        }
+#else
         __syncwarp();
         if (tile_end || jt == ntop) {
           fence_proxy_async();
@@ -576,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_ir_kernel(const __grid_cons
         } else if (lane == 0) {
           asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(done_addr), "r"((uint32_t)jt) : "memory");
         }
+#endif
         T(14);
       };
       uint2 r0[NC + 2], r1[NC + 2], r2[NC + 2];
