@@ -33,7 +33,7 @@ extern "C" {
 #define CASYNC_OK 0
 #define CASYNC_EINVAL (-1)   /* bad argument (shape / null pointer / unknown name) */
 #define CASYNC_ECUDA (-2)    /* a CUDA runtime call or launch failed                */
-#define CASYNC_EDEVICE (-3)  /* current device is not compute capability 10.x      */
+#define CASYNC_EDEVICE (-3)  /* current device is not compute capability 10.x, or is not the plan's device */
 #define CASYNC_EUNSUP (-4)   /* requested mode not implemented (e.g. fp32 path)     */
 
 /* casync_forward flags */
