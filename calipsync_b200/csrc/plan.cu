@@ -209,6 +209,7 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
+  bool strip_tc = true;              // ... with the depthwise conv on the tensor cores (strip_tc.cu); CASYNC_STRIPTC=0 disables
   bool strip_ir = true;              // strip-streaming fused blocks (strip_ir.cu); CASYNC_STRIP=0 falls back to fused_ir.cu
   std::vector<float> ir_b1, ir_b2;   // host copies of the folded-BN biases b1 / b2 of every InvertedResidual (128 floats each,
                                     // zero padded): the strip kernel takes them as kernel parameters
@@ -427,8 +428,10 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   const IrDef& d = kIr[idx];
   const std::string pre = std::string(d.name) + "|";
   const int hid = 2 * d.cin, H = d.h_in, Ho = d.stride == 2 ? H / 2 : H;
-  if (p->fuse_ir && p->strip_ir && !post_s && ldc == d.cout &&
-      strip_ir_supported(d.cin, d.cout, H, d.stride, up_low != nullptr, d.res)) {
+  const bool use_tc = p->fuse_ir && p->strip_tc && !post_s && ldc == d.cout &&
+                      strip_tc_supported(d.cin, d.cout, H, d.stride, up_low != nullptr, d.res);
+  if (use_tc || (p->fuse_ir && p->strip_ir && !post_s && ldc == d.cout &&
+                 strip_ir_supported(d.cin, d.cout, H, d.stride, up_low != nullptr, d.res))) {
     StripArgs f{};
     f.in = in;
     f.low = up_low;
@@ -441,10 +444,11 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     memcpy(f.b1, &p->ir_b1[(size_t)idx * 128], sizeof f.b1);
     memcpy(f.b2, &p->ir_b2[(size_t)idx * 128], sizeof f.b2);
     CK(chain_flush(p, st));
-    CK(launch_strip_ir(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res,
-                       g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms, st));
+    const int sms = g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms;
+    if (use_tc) CK(launch_strip_tc(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
+    else CK(launch_strip_ir(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
     const double px_in = (double)batch * H * H, px_out = (double)batch * Ho * Ho;
-    prof_mark((short_name(d.name) + ".strip").c_str(), 2.0 * px_in * d.cin * hid + 18.0 * px_out * hid + 2.0 * px_out * hid * d.cout,
+    prof_mark((short_name(d.name) + (use_tc ? ".striptc" : ".strip")).c_str(), 2.0 * px_in * d.cin * hid + 18.0 * px_out * hid + 2.0 * px_out * hid * d.cout,
               2.0 * (px_in * d.cin * (up_low ? 0.625 : 1.0) + px_out * d.cout * (d.res ? 2 : 1)));
     return 0;
   }
@@ -843,6 +847,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   }
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_STRIP")) p->strip_ir = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_STRIPTC")) p->strip_tc = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_DWEPI")) p->dw_epi = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_CHAIN")) p->use_chain = atoi(c) > 0;        // opt in to layer-program launches
   if (const char* c = getenv("CASYNC_NO_CHAIN")) p->use_chain = !(atoi(c) > 0);   // (dev harness spelling)
@@ -986,7 +991,8 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
     const bool up = i >= IR_UP && !((i - IR_UP) & 1);
     const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) &&
                        (fused_ir_supported(d.cin, d.cout, d.stride, up, d.res) ||
-                        (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
+                        (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)) ||
+                        (plan->strip_tc && strip_tc_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
     const bool dwe = plan->dw_epi && !plan->use_chain && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
     per_chunk += fused ? 1 : dwe ? 2 : 3;
   }

@@ -21,5 +21,9 @@ struct StripArgs {
 int launch_strip_ir(const StripArgs& a, int cin, int cout, int W, int stride, bool upcat, bool res, int num_sms,
                     cudaStream_t st);
 bool strip_ir_supported(int cin, int cout, int W, int stride, bool upcat, bool res);
+// strip_tc.cu: the same block with the depthwise 3x3 on the tensor cores (64 hidden channels)
+int launch_strip_tc(const StripArgs& a, int cin, int cout, int W, int stride, bool upcat, bool res, int num_sms,
+                    cudaStream_t st);
+bool strip_tc_supported(int cin, int cout, int W, int stride, bool upcat, bool res);
 
 }  // namespace casync
