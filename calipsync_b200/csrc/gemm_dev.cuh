@@ -1,5 +1,4 @@
-// Device helpers shared by the GEMM kernels (gemm_tc.cu: one layer per launch; chain.cu: a program of layers per
-// launch): bilinear taps of the decoder's upsample + concat producer, 2-D TMA tensor copies.
+// Device helpers of the GEMM kernel (gemm_tc.cu): bilinear taps of the decoder's upsample + concat producer, 2-D TMA tensor copies.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>

@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "../../include/casync_b200.h"
-#include "chain.cuh"
 #include "fused_ir.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -43,18 +42,8 @@ std::string g_gemm_dbg_match;
 unsigned long long* gemm_dbg_for(const std::string& label) {
   return g_gemm_dbg && label.find(g_gemm_dbg_match) != std::string::npos ? g_gemm_dbg : nullptr;
 }   // CTA cap of persistent kernels while two branches of the forward share the GPU
-// layers collected into a pending chain program have not run yet: their records are merged into one at the flush
-thread_local int g_pending = 0;
-thread_local double g_pend_flops = 0, g_pend_bytes = 0;
-thread_local char g_pend_first[40] = "";
 void prof_mark(const char* label, double flops, double bytes) {
   if (!g_prof) return;
-  if (g_pending > 0) {
-    if (g_pend_flops == 0 && g_pend_bytes == 0) snprintf(g_pend_first, sizeof g_pend_first, "%s", label);
-    g_pend_flops += flops;
-    g_pend_bytes += bytes;
-    return;
-  }
   casync_launch_record r{};
   snprintf(r.name, sizeof r.name, "%s", label);
   r.flops = flops;
@@ -134,7 +123,7 @@ const std::vector<Entry>& schema() {
     s.push_back({p + "bd", (size_t)hid * 4});
     s.push_back({p + "w2", packed_bytes(d.cout, hid)});
     s.push_back({p + "b2", (size_t)d.cout * 4});
-    s.push_back({p + "wdp", (size_t)hid * 10 * 2});   // depthwise taps + bias as bf16 [hid/8][10][8] (layer programs)
+    s.push_back({p + "wdp", (size_t)hid * 10 * 2});   // depthwise taps + bias as bf16 [hid/8][10][8]
   }
   s.push_back({"audio_model.conv3|w", packed_bytes(256, 9 * 128)});
   s.push_back({"audio_model.conv3|b", 256 * 4});
@@ -199,7 +188,7 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
 struct casync_plan {
-  mutable std::mutex mu;            // one forward / stage call at a time: lanes, events, graph cache and chain state are shared
+  mutable std::mutex mu;            // one forward / stage call at a time: lanes, events and the graph cache are shared
   int device = 0;                   // the CUDA device the plan was created on (streams, events, graphs live there)
   const uint8_t* dev = nullptr;
   std::vector<int64_t> off;
@@ -233,20 +222,7 @@ struct casync_plan {
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_lane_go = nullptr, ev_lane_done = nullptr;
   unsigned long long* phase_dbg = nullptr;   // developer timing only (CASYNC_PHASE_DBG=<ir index>)
   int phase_dbg_ir = -1;
-  // layer-program launches (chain.cu): consecutive GEMM / depthwise layers are collected and run as ONE launch
-  bool use_chain = false;           // CASYNC_CHAIN=1: opt in.  Measured at batch 64 (B200): 2.85 ms per forward against
-                                    // 2.42 ms with one launch per layer -- bit-exact, 24 launches instead of 76, but the
-                                    // in-order per-CTA item queues serialise the GEMM and depthwise phases of a block
-                                    // (DESIGN.md 3.4); default off until the item schedule is skewed
-  struct ChainSlot {                // device copy of the descriptors + counters of the i-th program of a forward;
-    void* dev = nullptr;            // plan-owned (a few hundred KB), re-uploaded only when the program changes
-    size_t cap = 0;
-    std::vector<unsigned char> last;
-  };
   mutable long launches_chunk = 0;  // kernels the last forward launched per chunk (measured)
-  mutable Chain chain;
-  mutable std::vector<ChainSlot> slots;
-  mutable int seg = 0, seg_base = 0;
   // CUDA graphs: a forward is 70-140 launches plus fork / join events; below batch ~16 the host cannot enqueue them as
   // fast as the GPU retires them (batch 8: 0.39 ms of enqueue per 0.62 ms step).  The launch sequence only depends on
   // (x, audio, out, workspace, batch, flags), so the second call with the same key is captured from the caller's stream
@@ -272,8 +248,6 @@ struct casync_plan {
   mutable std::vector<GraphKey> seen;
   mutable unsigned long long graph_tick = 0;
   mutable long graph_replays = 0, graph_captures = 0;
-  mutable unsigned char* arena = nullptr;   // hidden tensors of the InvertedResidual blocks inside one program: every
-  mutable size_t arena_cap = 0, arena_off = 0;   // buffer is written once per launch (no WAR hazards between items)
   template <class T>
   const T* w(const std::string& name) const {
     int i = entry_index(name);
@@ -309,118 +283,6 @@ struct Workspace {
     if (e_) return fail(CASYNC_ECUDA, "%s failed: %s", #expr, cudaGetErrorString((cudaError_t)e_)); \
   } while (0)
 
-// ---- layer-program plumbing (chain.cu) ---------------------------------------------------------------------------
-// GEMM / depthwise layers are appended to the plan's pending program; anything else (fused blocks, attention core,
-// element-wise kernels) first flushes it.  A program of one GEMM runs through the single-layer kernel.
-int chain_flush(const casync_plan* p, cudaStream_t st, bool keep_arena = false) {
-  Chain& c = p->chain;
-  if (c.empty()) return 0;
-  const int n = (int)c.size();
-  int e = 0;
-  if (n == 1 && c.kind(0) == CK_GEMM) {
-    const GemmArgs g = c.gemm(0);
-    c.reset();
-    e = launch_gemm(g, st);
-  } else {
-    if ((int)p->slots.size() <= p->seg) p->slots.resize(p->seg + 1);
-    casync_plan::ChainSlot& sl = p->slots[p->seg];
-    const size_t need = c.scratch_bytes();
-    if (need > sl.cap) {   // first use / larger batch: (re)allocate the descriptor + counter block
-      if (sl.dev) cudaFree(sl.dev);
-      sl.dev = nullptr;
-      sl.cap = 0;
-      sl.last.clear();
-      const size_t cap = (need + 65535) & ~(size_t)65535;
-      if (cudaMalloc(&sl.dev, cap) != cudaSuccess) {
-        c.reset();
-        return (int)cudaErrorMemoryAllocation;
-      }
-      sl.cap = cap;
-    }
-    static const bool dbg_sync = getenv("CASYNC_CHAIN_SYNC") && atoi(getenv("CASYNC_CHAIN_SYNC")) > 0;
-    std::string desc;
-    if (dbg_sync)   // developer aid: synchronise after every program and name the one that failed
-      for (int i = 0; i < n; ++i) {
-        const GemmArgs& g = c.gemm(i);
-        char b[96];
-        snprintf(b, sizeof b, " [%d %s M%d K%d N%d a%d s%d]", i, c.kind(i) == CK_DW ? "dw" : "gemm", g.M, g.K, g.N, g.amode, g.stride);
-        desc += b;
-      }
-    e = c.launch(sl.dev, sl.cap, sl.last, st);
-    if (dbg_sync && !e) {
-      cudaError_t se = cudaStreamSynchronize(st);
-      fprintf(stderr, "[chain sync] program %d (%d layers): %s%s\n", p->seg, n, cudaGetErrorString(se), se ? desc.c_str() : "");
-      if (se) e = (int)se;
-    }
-  }
-  ++p->seg;
-  // hidden tensors handed out before a flush in the middle of a block are still in use by the next program
-  if (!keep_arena) p->arena_off = 0;
-  if (g_prof && g_pending > 0) {
-    g_pending = 0;
-    char label[40];
-    snprintf(label, sizeof label, "chain%d[%d]:%.20s", p->seg - 1, n, g_pend_first);
-    prof_mark(label, g_pend_flops, g_pend_bytes);
-  }
-  g_pending = 0;
-  g_pend_flops = g_pend_bytes = 0;
-  return e;
-}
-
-int emit_gemm(const casync_plan* p, const GemmArgs& g, cudaStream_t st) {
-  if (!p->use_chain) return launch_gemm(g, st);
-  if (p->chain.add_gemm(g) == 0) {
-    ++g_pending;
-    return 0;
-  }
-  int e = chain_flush(p, st, true);
-  if (e) return e;
-  if (p->chain.add_gemm(g) == 0) {
-    ++g_pending;
-    return 0;
-  }
-  return launch_gemm(g, st);
-}
-
-int emit_dw(const casync_plan* p, const bf16* in, bf16* out, const uint8_t* wdp, int batch, int H, int C, int stride,
-            cudaStream_t st) {
-  static const int nodw = getenv("CASYNC_CHAIN_NODW") ? atoi(getenv("CASYNC_CHAIN_NODW")) : 0;   // developer A/B switch:
-  if (p->use_chain && !(nodw == 1 || nodw == 1 + stride)) {   // 1: no depthwise layers in programs, 2 / 3: not stride 1 / 2
-    if (p->chain.add_dw(in, out, wdp, batch, H, H, C, stride) == 0) {
-      ++g_pending;
-      return 0;
-    }
-    int e = chain_flush(p, st, true);
-    if (e) return e;
-    if (p->chain.add_dw(in, out, wdp, batch, H, H, C, stride) == 0) {
-      ++g_pending;
-      return 0;
-    }
-  }
-  int e = chain_flush(p, st, true);
-  if (e) return e;
-  return launch_dw3x3(in, out, wdp, batch, H, H, C, stride, st);
-}
-
-// hidden tensor of an InvertedResidual inside a program: a fresh piece of the arena (the h1 | h2 region), so that no
-// buffer is written twice within one launch.  nullptr: does not fit (caller flushes and retries, or uses h1 / h2).
-bf16* arena_alloc(const casync_plan* p, size_t elems) {
-  const size_t bytes = (elems * 2 + 255) & ~(size_t)255;
-  if (!p->arena || p->arena_off + bytes > p->arena_cap) return nullptr;
-  bf16* r = reinterpret_cast<bf16*>(p->arena + p->arena_off);
-  p->arena_off += bytes;
-  return r;
-}
-void chain_begin(const casync_plan* p, const Workspace& w, int frames) {
-  p->chain.reset();
-  p->seg = p->seg_base;   // each lane of a split batch has its own descriptor slots
-  p->arena = reinterpret_cast<unsigned char*>(w["h1"]);
-  p->arena_cap = (w.offs[w.index("h2")] - w.offs[w.index("h1")]) + align256((size_t)25600 * 128 * 2 * frames);
-  p->arena_off = 0;
-  g_pending = 0;
-  g_pend_flops = g_pend_bytes = 0;
-}
-
 // One InvertedResidual: pw1 GEMM (+BN+leaky) -> depthwise 3x3 (+BN+leaky) -> pw2 GEMM (+BN+leaky, +skip,
 // optional trailing BN).  `up_low` != null selects the decoder A producer: in = cat([up(up_low), in]).
 int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf16* out, int ldc, bf16* h1, bf16* h2,
@@ -443,7 +305,6 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     f.dbg = (p->phase_dbg && p->phase_dbg_ir == idx) ? p->phase_dbg : nullptr;
     memcpy(f.b1, &p->ir_b1[(size_t)idx * 128], sizeof f.b1);
     memcpy(f.b2, &p->ir_b2[(size_t)idx * 128], sizeof f.b2);
-    CK(chain_flush(p, st));
     const int sms = g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms;
     if (use_tc) CK(launch_strip_tc(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
     else CK(launch_strip_ir(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
@@ -474,26 +335,11 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     f.upcat = up_low != nullptr;
     f.res = d.res;
     f.dbg = (p->phase_dbg && p->phase_dbg_ir == idx) ? p->phase_dbg : nullptr;
-    CK(chain_flush(p, st));
     CK(launch_fused_ir(f, st));
     const double px_in = (double)batch * H * H, px_out = (double)batch * Ho * Ho;
     prof_mark((short_name(d.name) + ".fused").c_str(), 2.0 * px_in * d.cin * hid + 18.0 * px_out * hid + 2.0 * px_out * hid * d.cout,
               2.0 * (px_in * d.cin * (up_low ? 0.625 : 1.0) + px_out * d.cout * (d.res ? 2 : 1)));
     return 0;
-  }
-  if (p->use_chain) {   // hidden tensors from the arena: written once per program
-    const size_t n1 = (size_t)batch * H * H * hid, n2 = (size_t)batch * Ho * Ho * hid;
-    bf16* a1 = arena_alloc(p, n1);
-    bf16* a2 = a1 ? arena_alloc(p, n2) : nullptr;
-    if (!a2) {
-      CK(chain_flush(p, st));
-      a1 = arena_alloc(p, n1);
-      a2 = a1 ? arena_alloc(p, n2) : nullptr;
-    }
-    if (a2) {
-      h1 = a1;
-      h2 = a2;
-    }
   }
   GemmArgs g{};
   g.M = batch * H * H;
@@ -521,19 +367,19 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   const std::string sn = short_name(d.name);
   // 10x10 stages: frame-aligned row tiles (100 pixels), the depthwise conv runs in the GEMM's epilogue from a hidden tile
   // in shared memory -- one launch and one 13-26 MB round trip less per block
-  const bool dwe = p->dw_epi && !p->use_chain && !up_low && d.stride == 1 && H * H <= 100 && hid % 256 == 0;
+  const bool dwe = p->dw_epi && !up_low && d.stride == 1 && H * H <= 100 && hid % 256 == 0;
   if (dwe) {
     g.dw_epi = 1;
     g.dw_w = H;
     g.dwp = p->w<uint8_t>(pre + "wdp");
     g.C = h2;
   }
-  CK(emit_gemm(p, g, st));
+  CK(launch_gemm(g, st));
   if (dwe) {
     prof_mark((sn + ".pw1dw").c_str(), 2.0 * g.M * g.K * g.N + 18.0 * batch * Ho * Ho * hid, 2.0 * g.M * (g.K + g.N));
   } else {
     prof_mark((sn + ".pw1").c_str(), 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
-    CK(emit_dw(p, h1, h2, p->w<uint8_t>(pre + "wdp"), batch, H, hid, d.stride, st));
+    CK(launch_dw3x3(h1, h2, p->w<uint8_t>(pre + "wdp"), batch, H, H, hid, d.stride, st));
     prof_mark((sn + ".dw").c_str(), 18.0 * batch * Ho * Ho * hid, 2.0 * batch * hid * (H * H + Ho * Ho));
   }
   GemmArgs g2{};
@@ -556,7 +402,7 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g2.ldc = ldc;
   g2.max_ctas = g_cap;
   g2.dbg = gemm_dbg_for(short_name(d.name) + ".pw2");
-  CK(emit_gemm(p, g2, st));
+  CK(launch_gemm(g2, st));
   prof_mark((sn + ".pw2").c_str(), 2.0 * g2.M * g2.K * g2.N, 2.0 * g2.M * (g2.K + g2.N * (d.res ? 2 : 1)));
   return 0;
 }
@@ -582,7 +428,7 @@ int run_dense(const casync_plan* p, const char* wname, const char* bname, const 
   g.ldc = ldc;
   g.max_ctas = g_cap;
   g.dbg = gemm_dbg_for(wname);
-  CK(emit_gemm(p, g, st));
+  CK(launch_gemm(g, st));
   prof_mark(wname, 2.0 * M * K * N, 2.0 * M * (K + N * (res_pre ? 2 : 1)));
   return 0;
 }
@@ -606,25 +452,21 @@ int run_conv3x3(const casync_plan* p, const char* pre, const bf16* in, int Hin, 
   g.C = out;
   g.ldc = Cout;
   g.max_ctas = g_cap;
-  CK(emit_gemm(p, g, st));
+  CK(launch_gemm(g, st));
   prof_mark(pre, 2.0 * g.M * g.K * g.N, 2.0 * (batch * Hin * Hin * Cin + (double)g.M * Cout));
   return 0;
 }
 
 // AudioConvHubert.forward (module/unet.py:177-194); result (after bn7 + leaky) -> out[., ldo].
-// part 0: everything; 1: head only (layout change + the two fused 32x32 blocks); 2: tail only (conv3 ... conv7, the
-// layers that join the low-resolution layer program).
 int run_audio(const casync_plan* p, const float* audio, bf16* out, int ldo, const Workspace& w, int batch,
-              cudaStream_t st, int part = 0) {
+              cudaStream_t st) {
   int e;
-  if (part != 2) {
-    CK(chain_flush(p, st));
+  {
     CK(launch_audio_prep(audio, w["aud_in"], batch, st));
     prof_mark("audio.prep", 0, 6.0 * batch * 32768);
     if ((e = run_ir(p, IR_AUD1, w["aud_in"], nullptr, w["a1"], 64, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
     if ((e = run_ir(p, IR_AUD2, w["a1"], nullptr, w["a2"], 128, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
   }
-  if (part == 1) return 0;
   if ((e = run_conv3x3(p, "audio_model.conv3", w["a2"], 32, 128, 1, 256, w["a3"], batch, st))) return e;
   if ((e = run_ir(p, IR_AUD4, w["a3"], nullptr, w["a4"], 256, w["ah1"], w["ah2"], nullptr, nullptr, batch, st))) return e;
   if ((e = run_conv3x3(p, "audio_model.conv5", w["a4"], 16, 256, 3, 512, w["a5"], batch, st))) return e;
@@ -652,7 +494,7 @@ int run_kv(const casync_plan* p, const bf16* cat, const Workspace& w, int batch,
   g.vt = w["vt"];
   g.vt_col0 = 256;
   g.max_ctas = g_cap;
-  CK(emit_gemm(p, g, st));
+  CK(launch_gemm(g, st));
   prof_mark("attention_blocks|kv_w", 2.0 * g.M * g.K * g.N, 2.0 * g.M * (g.K + g.N));
   return 0;
 }
@@ -672,7 +514,6 @@ int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const 
     const std::string pre = "attention_blocks." + std::to_string(j) + "|";
     if ((e = run_dense(p, (pre + "p1q_w").c_str(), (pre + "p1q_b").c_str(), ox, 1024, M, 1024, 576, w["p1q"], 576, 0,
                        nullptr, 0, nullptr, st))) return e;
-    CK(chain_flush(p, st));
     CK(launch_attention(w["p1q"] + 512, 576, w["kall"] + j * 64, 256, w["vt"] + (size_t)j * 512 * 128, w["p1q"], 576,
                         w["att"], p->gamma[j], batch, st));
     prof_mark(("attn" + std::to_string(j) + ".core").c_str(), 2.0 * batch * (100.0 * 100 * 64 + 100.0 * 100 * 512),
@@ -681,7 +522,6 @@ int run_fusion_attention(const casync_plan* p, const bf16* cat, bf16* kx, const 
                        w["tx"], 1024, (pre + "b1_rs").c_str(), st))) return e;
     ox = w[oxn[j]];
   }
-  CK(chain_flush(p, st));
   CK(launch_sum5(w["tx"], w["ox0"], w["ox1"], w["ox2"], w["ox3"], p->w<float>("bn_kx|s"), p->w<float>("bn_kx|t"), kx,
                  M, st));
   prof_mark("sum5_bn_kx", 0, 2.0 * M * 1024 * 6);
@@ -707,7 +547,6 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     long l0;
     ~Count() { p->launches_chunk = launch_counter() - l0; }
   } count{p, launches0};
-  chain_begin(p, w, batch);
   CK(launch_inc(x, w["x1"], p->w<uint8_t>("inc.inconv.0|w2t"), p->inc, batch, st));
   prof_mark("inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
@@ -716,8 +555,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   // The audio encoder (and the key/value GEMM behind it) is independent of the face encoder.  Its kernels and the
   // low-resolution half of the face encoder are both latency-bound at small batch, so they run side by side: the
   // audio branch on the plan's side stream, each branch's persistent kernels capped to half of the SMs.
-  // With layer programs (chain.cu) the two branches are simply consecutive layers of ONE launch whose items interleave.
-  const bool overlap = !p->use_chain && p->overlap && side && !g_prof && batch <= p->overlap_max_batch;
+  const bool overlap = p->overlap && side && !g_prof && batch <= p->overlap_max_batch;
   auto down_block = [&](int l) -> int {
     const int i0 = IR_DOWN + 2 * l;
     int e2;
@@ -743,17 +581,6 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     if (e) return e;
     CK(cudaEventRecord(ev_join, side));
     CK(cudaStreamWaitEvent(st, ev_join, 0));
-  } else if (p->use_chain) {
-    // fused / element-wise launches first, so that every low-resolution layer up to the first attention core joins
-    // one program: down2.1 ... down4.1, audio conv3 ... conv7, MLP fusion, key/value and p_1/q projections
-    const int i0 = IR_DOWN + 2;
-    if ((e = run_ir(p, i0, cur, nullptr, w[dn_t[1]], kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
-    if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st, 1))) return e;
-    if ((e = run_ir(p, i0 + 1, w[dn_t[1]], nullptr, w[dn_o[1]], kIr[i0 + 1].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st))) return e;
-    cur = w[dn_o[1]];
-    for (int l = 2; l < 4; ++l)
-      if ((e = down_block(l))) return e;
-    if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st, 2))) return e;
   } else {
     for (int l = 1; l < 4; ++l)
       if ((e = down_block(l))) return e;
@@ -768,7 +595,6 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   if ((e = run_up(p, 2, w["up1"], w["x3"], w["t_up2"], w["up2"], w, batch, st))) return e;
   if ((e = run_up(p, 3, w["up2"], w["x2"], w["t_up3"], w["up3"], w, batch, st))) return e;
   if ((e = run_up(p, 4, w["up3"], w["x1"], w["t_up4"], w["up4"], w, batch, st))) return e;
-  CK(chain_flush(p, st));
   CK(launch_outc(w["up4"], out, p->outc, batch, (flags & CASYNC_F_OUT_U8_HWC) ? 1 : 0, st));
   prof_mark("outc.sigmoid", 2.0 * batch * 25600 * 96, batch * 25600.0 * (64 + ((flags & CASYNC_F_OUT_U8_HWC) ? 3 : 12)));
   return 0;
@@ -814,7 +640,6 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   if (e) return e;
   CK(gemm_init());
   CK(kernels_init());
-  CK(chain_init());
   casync_plan* p = new casync_plan;
   cudaGetDevice(&p->device);
   p->dev = reinterpret_cast<const uint8_t*>(dev_blob);
@@ -849,8 +674,6 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   if (const char* c = getenv("CASYNC_STRIP")) p->strip_ir = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_STRIPTC")) p->strip_tc = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_DWEPI")) p->dw_epi = atoi(c) > 0;
-  if (const char* c = getenv("CASYNC_CHAIN")) p->use_chain = atoi(c) > 0;        // opt in to layer-program launches
-  if (const char* c = getenv("CASYNC_NO_CHAIN")) p->use_chain = !(atoi(c) > 0);   // (dev harness spelling)
   if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
   if (const char* c = getenv("CASYNC_OVERLAP")) {   // A/B switch for the two-stream overlap (2: no CTA caps)
     p->overlap = atoi(c) > 0;
@@ -944,15 +767,12 @@ void casync_plan_destroy(casync_plan* plan) {
     cudaFree(g_gemm_dbg);
     g_gemm_dbg = nullptr;
   }
-  if (plan) chain_dbg_report();
   if (plan) {
     cudaDeviceSynchronize();   // replays / lanes of the last forward may still be running
     for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     plan->graphs.clear();
   }
   if (plan) {
-    for (auto& sl : plan->slots)
-      if (sl.dev) cudaFree(sl.dev);
     if (plan->side) {
       cudaStreamSynchronize(plan->side);
       cudaStreamDestroy(plan->side);
@@ -993,14 +813,13 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
                        (fused_ir_supported(d.cin, d.cout, d.stride, up, d.res) ||
                         (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)) ||
                         (plan->strip_tc && strip_tc_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
-    const bool dwe = plan->dw_epi && !plan->use_chain && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
+    const bool dwe = plan->dw_epi && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
     per_chunk += fused ? 1 : dwe ? 2 : 3;
   }
-  if (plan->use_chain && plan->launches_chunk > 0) per_chunk = plan->launches_chunk;   // layer programs: measured count
   int64_t total = 0;
   for (int f0 = 0; f0 < batch; f0 += plan->chunk) {
     const int nb = batch - f0 < plan->chunk ? batch - f0 : plan->chunk;
-    total += per_chunk * ((nb >= plan->split_min_batch && !plan->use_chain) ? 2 : 1);   // two lanes: every kernel twice
+    total += per_chunk * (nb >= plan->split_min_batch ? 2 : 1);   // two lanes: every kernel twice
   }
   return total;
 }
@@ -1014,20 +833,16 @@ static int forward_eager(const casync_plan* plan, const float* x, const float* a
     const float* xc = x + (size_t)f0 * 6 * 25600;
     const float* ac = audio + (size_t)f0 * 32768;
     uint8_t* oc = reinterpret_cast<uint8_t*>(out) + (size_t)f0 * out_frame;
-    // (layer programs are persistent 148-CTA launches that cannot share the GPU: measured 3.21 ms with both, 2.70 ms alone)
-    if (nb >= plan->split_min_batch && !plan->use_chain && !g_prof && plan->lane1) {
+    if (nb >= plan->split_min_batch && !g_prof && plan->lane1) {
       // two lanes: frames [0, h0) on the caller's stream, [h0, nb) on the plan's second stream, joined at the end
       const int hcap = (cap + 1) / 2, h0 = (nb + 1) / 2, h1 = nb - h0;
       Workspace w0(workspace, hcap);
       Workspace w1(reinterpret_cast<uint8_t*>(workspace) + w0.total, hcap);
       CK(cudaEventRecord(plan->ev_lane_go, st));
       CK(cudaStreamWaitEvent(plan->lane1, plan->ev_lane_go, 0));
-      plan->seg_base = 0;
       int e = forward_chunk(plan, xc, ac, oc, w0, h0, flags, st, 0);
-      plan->seg_base = 64;
       if (!e) e = forward_chunk(plan, xc + (size_t)h0 * 6 * 25600, ac + (size_t)h0 * 32768, oc + (size_t)h0 * out_frame, w1, h1,
                                 flags, plan->lane1, 1);
-      plan->seg_base = 0;
       CK(cudaEventRecord(plan->ev_lane_done, plan->lane1));
       CK(cudaStreamWaitEvent(st, plan->ev_lane_done, 0));
       if (e) return e;
@@ -1054,7 +869,7 @@ int casync_forward(const casync_plan* plan, const float* x, const float* audio, 
   int cur_dev = -1;
   if (cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev != plan->device)
     return fail(CASYNC_EDEVICE, "plan belongs to device %d but the current device is %d", plan->device, cur_dev);
-  if (!plan->use_graphs || plan->use_chain || g_prof) return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
+  if (!plan->use_graphs || g_prof) return forward_eager(plan, x, audio, out, workspace, batch, flags, st);
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
     cudaGetLastError();   // the caller is capturing this stream itself: our launches simply join its graph
@@ -1204,11 +1019,9 @@ int casync_ir_block(const casync_plan* plan, int ir_index, const void* in, void*
     return fail(CASYNC_EINVAL, "decoder block %d consumes (low, skip): use casync_up_block", ir_index);
   std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
-  chain_begin(plan, w, batch);
   int e = run_ir(plan, ir_index, reinterpret_cast<const bf16*>(in), nullptr, reinterpret_cast<bf16*>(out),
                  kIr[ir_index].cout, w["h1"], w["h2"], nullptr, nullptr, batch, reinterpret_cast<cudaStream_t>(stream));
   if (e) return e;
-  CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -1216,10 +1029,8 @@ int casync_audio_cnn(const casync_plan* plan, const float* audio, void* out, voi
   if (!plan || !audio || !out || !scratch || batch <= 0 || batch > plan->chunk) return fail(CASYNC_EINVAL, "bad argument");
   std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
-  chain_begin(plan, w, batch);
   int e = run_audio(plan, audio, reinterpret_cast<bf16*>(out), 512, w, batch, reinterpret_cast<cudaStream_t>(stream));
   if (e) return e;
-  CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -1233,10 +1044,8 @@ int casync_fusion_attention(const casync_plan* plan, const void* x5, const void*
   const size_t rows = (size_t)batch * 100;
   CK(cudaMemcpy2DAsync(w["cat"], 2048, x5, 1024, 1024, rows, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpy2DAsync(w["cat"] + 512, 2048, audio, 1024, 1024, rows, cudaMemcpyDeviceToDevice, st));
-  chain_begin(plan, w, batch);
   int e = run_fusion_attention(plan, w["cat"], reinterpret_cast<bf16*>(kx), w, batch, st);
   if (e) return e;
-  CK(chain_flush(plan, st));
   return 0;
 }
 
@@ -1247,11 +1056,9 @@ int casync_up_block(const casync_plan* plan, int level, const void* low, const v
   std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
   const char* tmp[4] = {"t_up1", "t_up2", "t_up3", "t_up4"};
-  chain_begin(plan, w, batch);
   int e = run_up(plan, level, reinterpret_cast<const bf16*>(low), reinterpret_cast<const bf16*>(skip), w[tmp[level - 1]],
                  reinterpret_cast<bf16*>(out), w, batch, reinterpret_cast<cudaStream_t>(stream));
   if (e) return e;
-  CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -1261,13 +1068,11 @@ int casync_up_first(const casync_plan* plan, int level, const void* low, const v
     return fail(CASYNC_EINVAL, "bad argument");
   std::lock_guard<std::mutex> guard(plan->mu);
   Workspace w(scratch, batch);
-  chain_begin(plan, w, batch);
   const int i0 = IR_UP + 2 * (level - 1);
   int e = run_ir(plan, i0, reinterpret_cast<const bf16*>(skip), reinterpret_cast<const bf16*>(low),
                  reinterpret_cast<bf16*>(out), kIr[i0].cout, w["h1"], w["h2"], nullptr, nullptr, batch,
                  reinterpret_cast<cudaStream_t>(stream));
   if (e) return e;
-  CK(chain_flush(plan, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -286,27 +286,6 @@ def test_host_pipeline_frames_mode():
         assert torch.equal(o, model.forward_uint8(x, a).cpu())
 
 
-@pytest.mark.parametrize("batch", [1, 5, 37])
-def test_layer_program_launches_are_bit_exact(batch, monkeypatch):
-    """CASYNC_CHAIN=1 runs the low-resolution GEMM / depthwise layers as layer programs (chain.cu: one persistent launch,
-    tile-granular dependency counters instead of kernel boundaries).  Same arithmetic in the same order: every stage
-    tensor and the output must equal the per-layer-launch path bit for bit (ragged row tiles included)."""
-    monkeypatch.setenv("CASYNC_SPLIT", "0")      # stage views describe the unsplit workspace layout
-    x, a = O.make_inputs(batch, 5)
-    model, _ = make_model("R1", seed=2)
-    ref = model(x.cuda(), a.cuda())
-    ref_stages = {n: model.stage(n, batch).clone() for n in ("x3", "x4", "x5", "audio", "tx", "kx", "fuse", "up1", "up2")}
-    monkeypatch.setenv("CASYNC_CHAIN", "1")
-    chained, _ = make_model("R1", seed=2)        # the switch is read when the plan is created
-    out = chained(x.cuda(), a.cuda())
-    assert chained.launches_per_forward(batch) < model.launches_per_forward(batch)
-    for n, t in ref_stages.items():
-        assert torch.equal(chained.stage(n, batch), t), n
-    assert torch.equal(out, ref)
-    out2 = chained(x.cuda(), a.cuda())           # second call: cached descriptors, re-zeroed counters
-    assert torch.equal(out2, ref)
-
-
 @pytest.mark.parametrize("batch", [25, 70])
 def test_two_lane_split_is_bit_exact(batch, monkeypatch):
     """Batches >= 24 run as two half-batches on two streams.  Frames are independent, so the result must

@@ -51,7 +51,7 @@ def test_folded_weights_reproduce_oracle(regime):
 def test_packed_depthwise_taps_layout():
     """`wdp` = depthwise taps + folded-BN bias as bf16, [hid/8][10][8]: entry (chunk, t, e) is tap t (t = 9: the bias)
     of channel 8*chunk + e, rounded fp64 -> fp32 -> bf16 exactly like the fp32 taps the fused kernel converts on the
-    device -- the stand-alone depthwise kernel, the weight-streaming fused blocks and the layer programs read it."""
+    device -- the stand-alone depthwise kernel, the weight-streaming fused blocks and the strip kernels read it."""
     sd = O.make_state_dict(0, "R1")
     entries = packer.build_entries(sd)
     for prefix, hid in (("down4.maxpool_conv.0.double_conv.1", 1024), ("audio_model.conv4", 512)):
