@@ -37,6 +37,10 @@ struct Prof {
 };
 thread_local Prof* g_prof = nullptr;
 thread_local int g_cap = 0;
+// output head fused into the last decoder block (strip_tc.cu): set by forward_chunk around run_up(4)
+thread_local void* g_final_out = nullptr;
+thread_local int g_final_u8 = 0;
+thread_local bool g_final_done = false;
 unsigned long long* g_gemm_dbg = nullptr;   // developer timing of the GEMM roles (CASYNC_GEMM_DBG=<label substring>)
 std::string g_gemm_dbg_match;
 unsigned long long* gemm_dbg_for(const std::string& label) {
@@ -198,6 +202,7 @@ struct casync_plan {
   int chunk = 256;
   int num_sms = 148;
   bool fuse_ir = true;
+  bool fuse_outc = true;             // OutConv + BN + sigmoid in the epilogue of up4.1 (CASYNC_FUSE_OUTC=0: own launch)
   bool strip_tc = true;              // ... with the depthwise conv on the tensor cores (strip_tc.cu); CASYNC_STRIPTC=0 disables
   bool strip_ir = true;              // strip-streaming fused blocks (strip_ir.cu); CASYNC_STRIP=0 falls back to fused_ir.cu
   std::vector<float> ir_b1, ir_b2;   // host copies of the folded-BN biases b1 / b2 of every InvertedResidual (128 floats each,
@@ -305,6 +310,13 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
     f.dbg = (p->phase_dbg && p->phase_dbg_ir == idx) ? p->phase_dbg : nullptr;
     memcpy(f.b1, &p->ir_b1[(size_t)idx * 128], sizeof f.b1);
     memcpy(f.b2, &p->ir_b2[(size_t)idx * 128], sizeof f.b2);
+    if (use_tc && g_final_out && idx == kNumIr - 1 && d.cout == 32) {   // up4.1: the output head runs in its epilogue
+      f.final_out = g_final_out;
+      f.final_u8 = g_final_u8;
+      memcpy(f.wo, p->outc.w, sizeof f.wo);
+      memcpy(f.bo, p->outc.b, sizeof f.bo);
+      g_final_done = true;
+    }
     const int sms = g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms;
     if (use_tc) CK(launch_strip_tc(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
     else CK(launch_strip_ir(f, d.cin, d.cout, H, d.stride, up_low != nullptr, d.res, sms, st));
@@ -594,7 +606,15 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
   if ((e = run_up(p, 1, w["fuse"], w["x4"], w["t_up1"], w["up1"], w, batch, st))) return e;
   if ((e = run_up(p, 2, w["up1"], w["x3"], w["t_up2"], w["up2"], w, batch, st))) return e;
   if ((e = run_up(p, 3, w["up2"], w["x2"], w["t_up3"], w["up3"], w, batch, st))) return e;
-  if ((e = run_up(p, 4, w["up3"], w["x1"], w["t_up4"], w["up4"], w, batch, st))) return e;
+  g_final_done = false;
+  if (p->fuse_outc && !g_prof) {
+    g_final_out = out;
+    g_final_u8 = (flags & CASYNC_F_OUT_U8_HWC) ? 1 : 0;
+  }
+  e = run_up(p, 4, w["up3"], w["x1"], w["t_up4"], w["up4"], w, batch, st);
+  g_final_out = nullptr;
+  if (e) return e;
+  if (g_final_done) return 0;   // (stage "up4" is not materialised on this path)
   CK(launch_outc(w["up4"], out, p->outc, batch, (flags & CASYNC_F_OUT_U8_HWC) ? 1 : 0, st));
   prof_mark("outc.sigmoid", 2.0 * batch * 25600 * 96, batch * 25600.0 * (64 + ((flags & CASYNC_F_OUT_U8_HWC) ? 3 : 12)));
   return 0;
@@ -673,6 +693,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_STRIP")) p->strip_ir = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_STRIPTC")) p->strip_tc = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_FUSE_OUTC")) p->fuse_outc = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_DWEPI")) p->dw_epi = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
   if (const char* c = getenv("CASYNC_OVERLAP")) {   // A/B switch for the two-stream overlap (2: no CTA caps)
@@ -816,6 +837,8 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
     const bool dwe = plan->dw_epi && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
     per_chunk += fused ? 1 : dwe ? 2 : 3;
   }
+  if (plan->fuse_outc && plan->fuse_ir && plan->strip_tc && strip_tc_supported(32, 32, 160, 1, false, true))
+    per_chunk -= 1;   // the output head runs in the epilogue of up4.1
   int64_t total = 0;
   for (int f0 = 0; f0 < batch; f0 += plan->chunk) {
     const int nb = batch - f0 < plan->chunk ? batch - f0 : plan->chunk;

@@ -15,6 +15,10 @@ struct StripArgs {
   unsigned long long* dbg;   // optional per-role cycle counters (developer timing, CASYNC_PHASE_DBG)
   float b1[128];             // folded-BN biases travel as kernel parameters: the drains add them straight from the
   float b2[128];             // constant bank (no shared-memory loads, no registers)
+  // strip_tc.cu, last decoder block only: OutConv + outc_bn + sigmoid (module/unet.py:100-106, 342-344) in the epilogue
+  void* final_out;           // fp32 NCHW [B,3,160,160] or uint8 HWC [B,160,160,3]; null: store the block's bf16 output
+  int final_u8;              // 1: uint8 HWC = floor(p * 255)
+  float wo[96], bo[3];       // folded OutConv weights [3][32] and biases
 };
 
 // cin/cout/W/stride/upcat/res select the instantiation.  Returns -1 when the block shape has none, else 0 / cudaError.

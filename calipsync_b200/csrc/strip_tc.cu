@@ -34,11 +34,11 @@ namespace {
 #if STRIP_TC_ORDER
 // the warp arbiter favours high warp ids: the three MMA issuers (a few instructions per tile, but every other role waits
 // for them) sit at the top
-constexpr int kProdWarp0 = 0, kEpiWarp0 = 4, kDrain1Warp0 = 12, kDrain2Warp0 = 20, kIssWarp0 = 28;
+constexpr int kProdWarp0 = 0, kEpiWarp0 = 4, kDrain1Warp0 = 8, kDrain2Warp0 = 16, kIssWarp0 = 24;
 #else
-constexpr int kIssWarp0 = 0, kEpiWarp0 = 4, kDrain1Warp0 = 12, kDrain2Warp0 = 20, kProdWarp0 = 28;
+constexpr int kIssWarp0 = 0, kEpiWarp0 = 4, kDrain1Warp0 = 8, kDrain2Warp0 = 16, kProdWarp0 = 24;
 #endif
-constexpr int kThreads = 32 * 32;
+constexpr int kThreads = 28 * 32;
 constexpr int kTileB = 16384;
 constexpr int kSleepNs = 64;
 #ifndef STRIP_EXP
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) strip_tc_kernel(const __grid_cons
       mbar_init(bar(B_A2FULL + i), 256);
       mbar_init(bar(B_A2FREE + i), 1);
       mbar_init(bar(B_D2FULL + i), 1);
-      mbar_init(bar(B_D2FREE + i), 256);
+      mbar_init(bar(B_D2FREE + i), 128);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(bar(B_HIDFULL + i), 256);
@@ -326,12 +326,11 @@ __global__ void __launch_bounds__(kThreads, 1) strip_tc_kernel(const __grid_cons
       fence_proxy_async();
       mbar_arrive(bar(B_A2FULL + b));
     }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
-    // =========================================== epilogue: D2 -> global (8 warps: lane quarter x column half) ===
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    // =========================================== epilogue: D2 -> global ========================================
     pdl_wait();
-    const int ew = warp - kEpiWarp0, lg = ew & 3, hw = ew >> 2;
-    const int row = lg * 32 + lane;
-    constexpr int NCE = COUT / 2;   // columns per thread
+    const int row = (warp - kEpiWarp0) * 32 + lane;
+    const bool fuse_outc = COUT == 32 && p.final_out != nullptr;   // last decoder block: the output head runs right here
     for (int t = 0; t < NT; ++t) {
       const int s = t & 1;
       const int q = t * 128 + row;
@@ -341,37 +340,34 @@ __global__ void __launch_bounds__(kThreads, 1) strip_tc_kernel(const __grid_cons
       const int b = bs / S, st = bs - b * S;
       const bool valid = jrow < ntop && hy < H && hx < SW && bs < p.batch * S;
       const size_t pix = valid ? ((size_t)b * H + hy) * W + st * SW + hx : 0;
-      uint4 rr[RES ? NCE / 8 : 1];
+      uint4 rr[RES ? COUT / 8 : 1];
       if constexpr (RES) {
 #pragma unroll
-        for (int i = 0; i < NCE / 8; ++i)
-          rr[i] = (valid && !(STRIP_EXP & 8)) ? __ldg(reinterpret_cast<const uint4*>(p.in + pix * CIN + hw * NCE + i * 8))
+        for (int i = 0; i < COUT / 8; ++i)
+          rr[i] = (valid && !(STRIP_EXP & 8)) ? __ldg(reinterpret_cast<const uint4*>(p.in + pix * CIN + i * 8))
                                               : make_uint4(0, 0, 0, 0);
       }
       mbar_wait_sleep<kSleepNs>(bar(B_D2FULL + s), (t >> 1) & 1);
       tc_fence_after();
+      float a0 = p.bo[0], a1 = p.bo[1], a2 = p.bo[2];   // OutConv accumulators (used when fuse_outc)
 #pragma unroll
-      for (int cc = 0; cc < NCE; cc += 16) {
-        uint32_t acc[16];
-        tmem_ld16(tD2 + s * COUT + hw * NCE + cc + ((uint32_t)(lg * 32) << 16), acc);
-        tmem_ld_wait16(acc);
-        if (cc + 16 >= NCE) {
+      for (int cc = 0; cc < COUT; cc += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tD2 + s * COUT + cc + ((uint32_t)((warp & 3) * 32) << 16), acc);
+        tmem_ld_wait32(acc);
+        if (cc + 32 >= COUT) {
           tc_fence_before();
           mbar_arrive(bar(B_D2FREE + s));
         }
         if (valid && !((STRIP_EXP & 8) && acc[0] != 0x12345u)) {
 #pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
+          for (int g8 = 0; g8 < 4; ++g8) {
             float vv[8];
-            if (hw == 0) {
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) vv[jj] = __uint_as_float(acc[g8 * 8 + jj]) + p.b2[cc + g8 * 8 + jj];
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) vv[jj] = __uint_as_float(acc[g8 * 8 + jj]) + p.b2[NCE + cc + g8 * 8 + jj];
+            for (int jj = 0; jj < 8; ++jj) {
+              vv[jj] = __uint_as_float(acc[g8 * 8 + jj]) + p.b2[cc + g8 * 8 + jj];
+              vv[jj] = fmaxf(vv[jj], kLeaky * vv[jj]);
             }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) vv[jj] = fmaxf(vv[jj], kLeaky * vv[jj]);
             if constexpr (RES) {
               const uint32_t* pr = &rr[(cc >> 3) + g8].x;
 #pragma unroll
@@ -380,8 +376,40 @@ __global__ void __launch_bounds__(kThreads, 1) strip_tc_kernel(const __grid_cons
                 vv[2 * jj + 1] += bf16_hi(pr[jj]);
               }
             }
-            *reinterpret_cast<uint4*>(p.out + pix * COUT + hw * NCE + cc + g8 * 8) =
-                make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]), pack_bf16(vv[4], vv[5]), pack_bf16(vv[6], vv[7]));
+            const uint4 o = make_uint4(pack_bf16(vv[0], vv[1]), pack_bf16(vv[2], vv[3]), pack_bf16(vv[4], vv[5]),
+                                       pack_bf16(vv[6], vv[7]));
+            if constexpr (COUT == 32) {
+              if (fuse_outc) {
+                // OutConv on the ROUNDED bf16 values in the order of outc_kernel: bit-identical to the two-launch path
+                const uint32_t* pv = &o.x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float lo = bf16_lo(pv[j]), hi = bf16_hi(pv[j]);
+                  const int c = g8 * 8 + 2 * j;
+                  a0 = fmaf(p.wo[c + 1], hi, fmaf(p.wo[c], lo, a0));
+                  a1 = fmaf(p.wo[32 + c + 1], hi, fmaf(p.wo[32 + c], lo, a1));
+                  a2 = fmaf(p.wo[64 + c + 1], hi, fmaf(p.wo[64 + c], lo, a2));
+                }
+                continue;
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + pix * COUT + cc + g8 * 8) = o;
+          }
+        }
+      }
+      if constexpr (COUT == 32) {
+        if (fuse_outc && valid) {
+          const float s0 = 1.f / (1.f + __expf(-a0)), s1 = 1.f / (1.f + __expf(-a1)), s2 = 1.f / (1.f + __expf(-a2));
+          if (p.final_u8) {   // floor(p * 255) like `np.array(pred * 255, dtype=np.uint8)` (infer_api.py:265-266)
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(p.final_out) + pix * 3;
+            o8[0] = (uint8_t)(s0 * 255.f);
+            o8[1] = (uint8_t)(s1 * 255.f);
+            o8[2] = (uint8_t)(s2 * 255.f);
+          } else {
+            float* of = reinterpret_cast<float*>(p.final_out) + (size_t)b * 76800 + (size_t)hy * W + st * SW + hx;
+            of[0] = s0;
+            of[25600] = s1;
+            of[51200] = s2;
           }
         }
       }

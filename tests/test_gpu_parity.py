@@ -32,7 +32,8 @@ def stage_nchw(model, name, batch):
 
 
 @pytest.mark.parametrize("regime", ["R0", "R1"])
-def test_forward_matches_golden_and_oracle_stages(regime):
+def test_forward_matches_golden_and_oracle_stages(regime, monkeypatch):
+    monkeypatch.setenv("CASYNC_FUSE_OUTC", "0")      # keep stage "up4" materialised (fused head: test below)
     model, sd = make_model(regime)
     x, a = O.make_inputs(2, 0)
     out = model(x.cuda(), a.cuda()).cpu()
@@ -64,6 +65,24 @@ def test_config2_batch64_tolerance(regime):
     print("\n[B=64] max-abs*255=%.4f PSNR=%.2f dB" % (O.max_abs_255(out, ref), O.psnr_db(out, ref)))
     assert O.max_abs_255(out, ref) <= MAX_ABS_255 and O.psnr_db(out, ref) >= MIN_PSNR
     assert min(O.psnr_db(out[i], ref[i]) for i in range(64)) >= MIN_PSNR
+
+
+@pytest.mark.parametrize("batch", [3, 40])
+def test_output_head_fused_into_the_last_decoder_block_is_bit_exact(batch, monkeypatch):
+    """OutConv + outc_bn + sigmoid (module/unet.py:342-344) run in the epilogue of up4.1 (no outc launch, the block's
+    bf16 output never reaches HBM).  The head is evaluated on the ROUNDED bf16 activations in the order of the stand-alone
+    kernel, so fp32 and uint8 outputs must equal the two-launch path bit for bit."""
+    x, a = O.make_inputs(batch, 15)
+    xs, as_ = x.cuda(), a.cuda()
+    fused, sd = make_model("R1", seed=8)
+    out_f, u8_f = fused(xs, as_), fused.forward_uint8(xs, as_)
+    monkeypatch.setenv("CASYNC_FUSE_OUTC", "0")
+    plain, _ = make_model("R1", seed=8)
+    assert torch.equal(out_f, plain(xs, as_))
+    assert torch.equal(u8_f, plain.forward_uint8(xs, as_))
+    assert fused.launches_per_forward(batch) == plain.launches_per_forward(batch) - (2 if batch >= 24 else 1)
+    ref = O.forward(sd, x, a)
+    assert O.max_abs_255(out_f.cpu(), ref) <= MAX_ABS_255 and O.psnr_db(out_f.cpu(), ref) >= MIN_PSNR
 
 
 def test_frames_are_independent_and_ragged_batches_work():
