@@ -117,6 +117,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   uint32_t sz = valid ? 16u : 0u;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {   // 4 bytes, zero fill when !valid
+  uint32_t sz = valid ? 4u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

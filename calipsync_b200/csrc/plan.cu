@@ -203,6 +203,7 @@ struct casync_plan {
   int num_sms = 148;
   bool fuse_ir = true;
   bool fuse_outc = true;             // OutConv + BN + sigmoid in the epilogue of up4.1 (CASYNC_FUSE_OUTC=0: own launch)
+  bool inc_tc = true;                // the input block as a strip_tc instantiation; CASYNC_INCTC=0: inc_kernel
   bool strip_tc = true;              // ... with the depthwise conv on the tensor cores (strip_tc.cu); CASYNC_STRIPTC=0 disables
   bool strip_ir = true;              // strip-streaming fused blocks (strip_ir.cu); CASYNC_STRIP=0 falls back to fused_ir.cu
   std::vector<float> ir_b1, ir_b2;   // host copies of the folded-BN biases b1 / b2 of every InvertedResidual (128 floats each,
@@ -559,8 +560,23 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     long l0;
     ~Count() { p->launches_chunk = launch_counter() - l0; }
   } count{p, launches0};
-  CK(launch_inc(x, w["x1"], p->w<uint8_t>("inc.inconv.0|w2t"), p->inc, batch, st));
-  prof_mark("inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
+  if (p->fuse_ir && p->inc_tc) {   // strip_tc.cu: all three convolutions of the input block on the tensor cores
+    StripArgs f{};
+    f.x_nchw = x;
+    f.out = w["x1"];
+    f.W2 = p->w<uint8_t>("inc.inconv.0|w2t");
+    f.batch = batch;
+    f.dbg = (p->phase_dbg && p->phase_dbg_ir == 0) ? p->phase_dbg : nullptr;
+    memcpy(f.inc_w1, p->inc.w1, sizeof f.inc_w1);
+    memcpy(f.inc_wd, p->inc.wd, sizeof f.inc_wd);
+    memcpy(f.inc_bd, p->inc.bd, sizeof p->inc.bd);
+    memcpy(f.b1, p->inc.b1, sizeof p->inc.b1);
+    memcpy(f.b2, p->inc.b2, sizeof p->inc.b2);
+    CK(launch_strip_inc(f, g_cap > 0 && g_cap < p->num_sms ? g_cap : p->num_sms, st));
+  } else {
+    CK(launch_inc(x, w["x1"], p->w<uint8_t>("inc.inconv.0|w2t"), p->inc, batch, st));
+  }
+  prof_mark(p->fuse_ir && p->inc_tc ? "inc.striptc" : "inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
   const char* dn_o[4] = {"x2", "x3", "x4", "cat"};
   const bf16* cur = w["x1"];
@@ -693,6 +709,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   if (const char* c = getenv("CASYNC_NO_FUSED_IR")) p->fuse_ir = !(atoi(c) > 0);
   if (const char* c = getenv("CASYNC_STRIP")) p->strip_ir = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_STRIPTC")) p->strip_tc = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_INCTC")) p->inc_tc = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_FUSE_OUTC")) p->fuse_outc = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_DWEPI")) p->dw_epi = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_NO_PDL")) pdl_enabled() = !(atoi(c) > 0);   // A/B switch for programmatic dependent launch
@@ -734,6 +751,31 @@ void casync_plan_destroy(casync_plan* plan) {
   if (plan) {   // synchronise and release on the plan's device, whatever the caller's current device is
     cudaGetDevice(&prev_dev);
     if (prev_dev != plan->device) cudaSetDevice(plan->device); else prev_dev = -1;
+  }
+  if (plan && plan->phase_dbg && plan->fuse_ir &&
+      ((plan->phase_dbg_ir == 0 && plan->inc_tc) ||
+       (plan->strip_tc && plan->phase_dbg_ir > 0 && plan->phase_dbg_ir < kNumIr &&
+        strip_tc_supported(kIr[plan->phase_dbg_ir].cin, kIr[plan->phase_dbg_ir].cout, kIr[plan->phase_dbg_ir].h_in,
+                           kIr[plan->phase_dbg_ir].stride, false, kIr[plan->phase_dbg_ir].res) &&
+        !(plan->phase_dbg_ir >= IR_UP && !((plan->phase_dbg_ir - IR_UP) & 1))))) {
+    unsigned long long h[32] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, plan->phase_dbg, 256, cudaMemcpyDeviceToHost);
+    const char* names[23] = {"P:issue", "P:land", "P:wait_a1free", "P:store", "I1:wait_a1full", "I1:wait_d1free", "I1:issue",
+                             "D1:wait_d1full", "D1:wait_hidfree", "D1:work", "IW:wait_hid", "IW:wait_hid+1", "IW:wait_dwfree",
+                             "IW:issue", "D2:wait_dwfull", "D2:wait_a2free", "D2:work", "I2:wait_a2full", "I2:wait_d2free",
+                             "I2:issue", "E:index", "E:wait_d2full", "E:work"};
+    const int lo[7] = {0, 4, 7, 10, 14, 17, 20}, hi[7] = {4, 7, 10, 14, 17, 20, 23};
+    fprintf(stderr, "[casync strip_tc dbg] ir %d (share of each role's own time):\n", plan->phase_dbg_ir);
+    for (int r = 0; r < 7; ++r) {
+      double tot = 0;
+      for (int i = lo[r]; i < hi[r]; ++i) tot += (double)h[i];
+      fprintf(stderr, "   ");
+      for (int i = lo[r]; i < hi[r]; ++i) fprintf(stderr, " %s=%.1f%%", names[i], 100.0 * h[i] / (tot > 0 ? tot : 1));
+      fprintf(stderr, "  [%.3g cycles]\n", tot);
+    }
+    cudaFree(plan->phase_dbg);
+    plan->phase_dbg = nullptr;
   }
   if (plan && plan->phase_dbg && plan->strip_ir && plan->phase_dbg_ir > 0 && plan->phase_dbg_ir < kNumIr &&
       strip_ir_supported(kIr[plan->phase_dbg_ir].cin, kIr[plan->phase_dbg_ir].cout, kIr[plan->phase_dbg_ir].h_in,

@@ -19,6 +19,11 @@ struct StripArgs {
   void* final_out;           // fp32 NCHW [B,3,160,160] or uint8 HWC [B,160,160,3]; null: store the block's bf16 output
   int final_u8;              // 1: uint8 HWC = floor(p * 255)
   float wo[96], bo[3];       // folded OutConv weights [3][32] and biases
+  // strip_tc.cu, `inc` instantiation (InConvDw, module/unet.py:58-67: 6 -> 12 -> 32 at 160x160, fp32 NCHW input)
+  const float* x_nchw;       // [B,6,160,160]
+  float inc_w1[72];          // [12 hidden][6 cin], BN folded (b1[] above holds the 12 biases)
+  float inc_wd[108];         // [9 taps][12 hidden]
+  float inc_bd[16];          // 12 biases, zero padded
 };
 
 // cin/cout/W/stride/upcat/res select the instantiation.  Returns -1 when the block shape has none, else 0 / cudaError.
@@ -29,5 +34,7 @@ bool strip_ir_supported(int cin, int cout, int W, int stride, bool upcat, bool r
 int launch_strip_tc(const StripArgs& a, int cin, int cout, int W, int stride, bool upcat, bool res, int num_sms,
                     cudaStream_t st);
 bool strip_tc_supported(int cin, int cout, int W, int stride, bool upcat, bool res);
+// strip_tc.cu: the input block (x_nchw, inc_*, b1, b2, W2 = the packed pw2 tile, out = x1 NHWC)
+int launch_strip_inc(const StripArgs& a, int num_sms, cudaStream_t st);
 
 }  // namespace casync
