@@ -224,6 +224,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// round to bf16, then LeakyReLU on the packed pair: max(v, slope * v) (slope = 1: identity)
+__device__ __forceinline__ uint32_t pack_leaky(float lo, float hi, __nv_bfloat162 slope2) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  v = __hmax2(v, __hmul2(v, slope2));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -16,6 +16,7 @@
 //                            LeakyReLU, pre/post residuals, trailing BN) with 16-byte bf16 stores, overlapping the
 //                            main loop of the CTA's next tile.
 // Grid = min(#tiles, #SMs); tiles are walked N-fastest so CTAs that share an A tile run at the same time.
+#include <cstdlib>
 #include "gemm_tc.cuh"
 #include "gemm_dev.cuh"
 
@@ -61,7 +62,8 @@ struct Cfg {
 //                    2 + scaled residual before the activation (fc2, b_1)   3 everything by run-time flags (kv, bn7)
 enum : int { EPI_PLAIN = 0, EPI_RES_POST = 1, EPI_RES_PRE = 2, EPI_GENERIC = 3 };
 template <int BN, bool DWE, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmC) {
   using C = Cfg<BN, DWE>;
   constexpr bool kGen = EPI == EPI_GENERIC;
   constexpr int S = C::S;
@@ -137,7 +139,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
     // Output rows go through a warp-private staging slab (32 rows x 64 B, 16-byte chunks XOR-swizzled by row pair) and
     // leave as 8 rows x 64 contiguous bytes per store instruction: a thread owns one accumulator ROW, so storing
     // straight from registers writes 32 half-filled sectors per instruction (measured: ~11k cycles per 128x256 tile).
-    uint8_t* const stg = smem_raw + (bar_base + 256 + 8192 - smem_u32(smem_raw)) + ew * 2048;
+    // The slab is a SWIZZLE_64B TMA box (32 columns x 32 rows): one elected lane ships it with a tensor store, which also
+    // clips the rows beyond M.  The XOR term is a function of the ABSOLUTE shared-memory address (bits 7-8).
+    const uint32_t stg_a = bar_base + 256 + 8192 + ew * 2048;
+    uint8_t* const stg = smem_raw + (stg_a - smem_u32(smem_raw));
+    const uint32_t sx = ((stg_a + lane * 64) >> 7) & 3;   // swizzle term of this thread's row
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
           for (int t9 = 0; t9 < 9; ++t9) wt[t9] = __ldg(tp + t9);
           wb = __ldg(tp + 9);
         }
+        const __nv_bfloat162 slope2 = __floats2bfloat162_rn(p.leaky ? kLeaky : 1.0f, p.leaky ? kLeaky : 1.0f);
         mbar_wait(acc_full(ab), (t >> 1) & 1);
         T(8);
         tc_fence_after();
@@ -188,13 +195,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
               const float4 b1 = *reinterpret_cast<const float4*>(ev + c0 + 8 * g + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
-                if (p.leaky) v[q] = fmaxf(v[q], kLeaky * v[q]);
-              }
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(acc[8 * g + q]) + bb[q];
               const uint32_t ci = (uint32_t)(c0 >> 3) + g;
               *reinterpret_cast<uint4*>(hid + r * (BN * 2) + ((ci ^ (uint32_t)(r & 7)) << 4)) =
-                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                  make_uint4(pack_leaky(v[0], v[1], slope2), pack_leaky(v[2], v[3], slope2), pack_leaky(v[4], v[5], slope2),
+                             pack_leaky(v[6], v[7], slope2));
             }
           }
         }
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
       const bool has_ps = kGen ? p.post_scale != nullptr : false;
       const bool has_vt = kGen ? (p.vt && n0 >= p.vt_col0) : false;
       const float slope = p.leaky ? kLeaky : 1.0f;   // max(v, 1 * v) == v: LeakyReLU on / off without a branch
+      const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
       const __nv_bfloat16* rsrc = has_pre ? p.res_pre + (size_t)m * p.ld_rpre : has_post ? p.res_post + (size_t)m * p.ld_rpost : nullptr;
       uint4 rnext[4];
       auto fetch_res = [&](int c0) {
@@ -269,6 +275,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
         }
         tmem_ld_wait32(acc);
         T(13);
+        if (!has_vt) {   // the previous chunk's tensor store has read the slab (its issuer waits, the warp follows)
+          if (elect_one()) tma_store_wait_read();
+          __syncwarp();
+        }
         if (row_ok) {
           const int n = n0 + c0;
           // all arithmetic first, the four staging stores after it: a shared-memory load (bias / scale vectors) cannot
@@ -300,10 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], kLeaky * v[q]);
               }
-            } else {
+            } else if constexpr (EPI != EPI_PLAIN) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], slope * v[q]);
-            }
+            }   // EPI_PLAIN: LeakyReLU on the packed bf16 pairs below (half the instructions)
             if (has_post) {
               const uint32_t* pr = &rcur[g].x;
 #pragma unroll
@@ -333,30 +343,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
               for (int q = 0; q < 8; ++q) dst[q * 128] = __float2bfloat16_rn(v[q]);
             } else {
               uint4& o = og[kDefer ? g : 0];
-              o.x = pack_bf16(v[0], v[1]);
-              o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]);
-              o.w = pack_bf16(v[6], v[7]);
-              if constexpr (!kDefer) *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = o;
+              if constexpr (EPI == EPI_PLAIN) {
+                o.x = pack_leaky(v[0], v[1], slope2);
+                o.y = pack_leaky(v[2], v[3], slope2);
+                o.z = pack_leaky(v[4], v[5], slope2);
+                o.w = pack_leaky(v[6], v[7], slope2);
+              } else {
+                o.x = pack_bf16(v[0], v[1]);
+                o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]);
+                o.w = pack_bf16(v[6], v[7]);
+              }
+              if constexpr (!kDefer) *reinterpret_cast<uint4*>(stg + lane * 64 + (((uint32_t)g ^ sx) << 4)) = o;
             }
           }
           if constexpr (kDefer) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = og[g];
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + lane * 64 + (((uint32_t)g ^ sx) << 4)) = og[g];
           }
         }
         T(14);
         if (!has_vt) {
+          fence_proxy_async();   // generic-proxy slab writes -> async proxy
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rl = i * 8 + (lane >> 2), c = lane & 3;
-            const uint4 o = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((c ^ ((rl >> 1) & 3)) << 4));
-            const int ml = m0 + lg * 32 + rl;
-            if (ml < p.M) *reinterpret_cast<uint4*>(p.C + (size_t)ml * p.ldc + n0 + c0 + 8 * c) = o;
-          }
-          __syncwarp();
+          if (elect_one()) tma_store_2d(&tmC, stg_a, n0 + c0, m0 + lg * 32);   // converged warp: same lane every time
         }
         T(15);
       }
@@ -364,6 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
       mbar_arrive(acc_empty(ab));
       T(9);
     }
+    __syncwarp();
+    if (elect_one()) tma_store_wait_read();   // shared memory must outlive the last tensor store
   };
 
   if (warp < 8 && p.amode == A_PLAIN) {
@@ -566,6 +578,19 @@ int gemm_encode_map(void* tm_out, const __nv_bfloat16* A, int rows, int cols, in
   return 0;
 }
 
+static int gemm_encode_store_map(void* tm_out, const __nv_bfloat16* Cp, int rows, int cols, int ld) {
+  if (!g_encode || (ld & 7) || ((uintptr_t)Cp & 15)) return (int)cudaErrorInvalidValue;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  if (g_encode(reinterpret_cast<CUtensorMap*>(tm_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(Cp),
+               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int)cudaErrorInvalidValue;
+  return 0;
+}
+
 int gemm_num_sms() { return g_num_sms; }
 
 namespace {
@@ -583,7 +608,14 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     const int e = gemm_encode_map(&tm, a.A, a.M, a.K, a.lda, kBM, true);
     if (e) return e;
   }
-  return (int)launch_pdl(gemm_tc_kernel<BN, DWE, EPI>, dim3(grid), dim3(kThreads), Cfg<BN, DWE>::kSmem, stream, a, tm);
+  // C[M, N] bf16 row-major with pitch ldc: box = 32 columns (64 B) x 32 rows, SWIZZLE_64B (the epilogue's staging slab)
+  alignas(64) CUtensorMap tc;
+  memset(&tc, 0, sizeof tc);
+  if (!DWE) {
+    const int e = gemm_encode_store_map(&tc, a.C, a.M, a.N, a.ldc);
+    if (e) return e;
+  }
+  return (int)launch_pdl(gemm_tc_kernel<BN, DWE, EPI>, dim3(grid), dim3(kThreads), Cfg<BN, DWE>::kSmem, stream, a, tm, tc);
 }
 
 template <int BN, bool DWE, int EPI>
@@ -659,7 +691,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
   int best = 32;
   double bc = tile_cost(mt, a.N, 32, cap);
+  static const int bn_max = getenv("CASYNC_GEMM_BNMAX") ? atoi(getenv("CASYNC_GEMM_BNMAX")) : 256;   // developer A/B
   for (int bn : {64, 128, 192, 256}) {   // 192: N = 576 (p_1 + q) -> 3 column tiles instead of 9
+    if (bn > bn_max) continue;
     if (a.vt && a.vt_col0 % bn) continue;   // a column tile must not straddle the row-major | transposed boundary
     const double c = tile_cost(mt, a.N, bn, cap);
     if (c <= bc) {
