@@ -1,5 +1,6 @@
 // CUDA-core kernels (sm_100a): fused `inc` block, depthwise 3x3, audio layout change, attention core,
 // stage sum + BN, output head.  All activations NHWC bf16, all arithmetic fp32.
+#include <cstdlib>
 #include "kernels.cuh"
 
 #include <cuda_bf16.h>
@@ -189,14 +190,14 @@ __global__ void __launch_bounds__(256) inc_kernel(const float* __restrict__ x, _
 constexpr int kDwSmemMax = 56 * 1024;       // band budget: four CTAs per SM
 constexpr int kDwSmemLimit = 100 * 1024;    // 160-pixel rows (unfused A/B path only): three input rows need 62 KB
 
-template <int STRIDE>
+template <int STRIDE, int FPC>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restrict__ in,
                                                     __nv_bfloat16* __restrict__ out, const uint4* __restrict__ wdp,
-                                                    int H, int W, int C, int Ho, int Wo, int BR) {
+                                                    int H, int W, int C, int Ho, int Wo, int BR, int batch) {
   extern __shared__ uint4 dw_tile[];   // [rows_in][W + 2][8 chunks of 8 channels]
   pdl_launch_dependents();
   const int tid = threadIdx.x, chunk = tid & 7;
-  const int c0 = blockIdx.x * 64, oy0 = blockIdx.y * BR, b = blockIdx.z;
+  const int c0 = blockIdx.x * 64, oy0 = blockIdx.y * BR, b0 = blockIdx.z * FPC;
   const int rows_out = BR < Ho - oy0 ? BR : Ho - oy0;
   const int rows_in = (rows_out - 1) * STRIDE + 3, TW = W + 2;
   const int iy0 = oy0 * STRIDE - 1;
@@ -212,41 +213,55 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const __nv_bfloat16* __restr
   }
   const __nv_bfloat162 kslope = __floats2bfloat162_rn(kLeaky, kLeaky);
   pdl_wait();   // the hidden tensor is the previous kernel's output
-  const __nv_bfloat16* ib = in + (size_t)b * H * W * C + c;
+  // FPC frames per CTA: every frame's band is requested up front (one cp.async group each), so the L2 latency is paid
+  // once per CTA and frame f is computed while frames f+1.. are still landing
   const uint32_t tile_s = smem_u32(dw_tile);
   const int npx = rows_in * TW;
-  for (int px = tid >> 3; px < npx; px += 32) {      // 256 % 8 == 0: a thread always copies its own chunk column
-    const int ty = px / TW, tx = px - ty * TW;
-    const int iy = iy0 + ty, ix = tx - 1;
-    const bool valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
-    cp_async16(tile_s + (uint32_t)(px * 8 + chunk) * 16u, valid ? ib + ((size_t)iy * W + ix) * C : ib, valid);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  const int nunits = rows_out * Wo;
-  __nv_bfloat16* ob = out + ((size_t)b * Ho + oy0) * Wo * C + c;
-  for (int p = tid >> 3; p < nunits; p += 32) {
-    const int oy = p / Wo, ox = p - oy * Wo;
-    const uint4* t0 = dw_tile + ((oy * STRIDE) * TW + ox * STRIDE) * 8 + chunk;
-    __nv_bfloat162 a[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = reinterpret_cast<const __nv_bfloat162*>(&wb)[q];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const uint4 v = t0[(ky * TW + kx) * 8];
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-        const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&wt[ky * 3 + kx]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = __hfma2(pw[q], pv[q], a[q]);
+  for (int f = 0; f < FPC; ++f) {
+    if (b0 + f < batch) {
+      const __nv_bfloat16* ib = in + (size_t)(b0 + f) * H * W * C + c;
+      for (int px = tid >> 3; px < npx; px += 32) {      // 256 % 8 == 0: a thread always copies its own chunk column
+        const int ty = px / TW, tx = px - ty * TW;
+        const int iy = iy0 + ty, ix = tx - 1;
+        const bool valid = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        cp_async16(tile_s + (uint32_t)((f * npx + px) * 8 + chunk) * 16u, valid ? ib + ((size_t)iy * W + ix) * C : ib, valid);
       }
-    uint4 o;
-    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+    }
+    cp_async_commit();
+  }
+  const int nunits = rows_out * Wo;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) po[q] = __hmax2(a[q], __hmul2(a[q], kslope));
-    *reinterpret_cast<uint4*>(ob + (size_t)p * C) = o;
+  for (int f = 0; f < FPC; ++f) {
+    if (f == 0) cp_async_wait<FPC - 1>();
+    else if (f == 1) cp_async_wait<(FPC > 2 ? FPC - 2 : 0)>();
+    else if (f == 2) cp_async_wait<(FPC > 3 ? FPC - 3 : 0)>();
+    else cp_async_wait<0>();
+    __syncthreads();
+    if (b0 + f >= batch) break;
+    __nv_bfloat16* ob = out + ((size_t)(b0 + f) * Ho + oy0) * Wo * C + c;
+    for (int p = tid >> 3; p < nunits; p += 32) {
+      const int oy = p / Wo, ox = p - oy * Wo;
+      const uint4* t0 = dw_tile + (f * npx + (oy * STRIDE) * TW + ox * STRIDE) * 8 + chunk;
+      __nv_bfloat162 a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = reinterpret_cast<const __nv_bfloat162*>(&wb)[q];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint4 v = t0[(ky * TW + kx) * 8];
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+          const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&wt[ky * 3 + kx]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = __hfma2(pw[q], pv[q], a[q]);
+        }
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) po[q] = __hmax2(a[q], __hmul2(a[q], kslope));
+      *reinterpret_cast<uint4*>(ob + (size_t)p * C) = o;
+    }
   }
 }
 
@@ -541,8 +556,12 @@ int kernels_init() {
   int e = (int)cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(AttnSmem) + 1024);
   e |= (int)cudaFuncSetAttribute(inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IncSmem) + 1024);
-  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
-  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
+  e |= (int)cudaFuncSetAttribute(dw3x3_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemLimit);
   return e;
 }
 
@@ -565,11 +584,25 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp
   if (BR > Ho) BR = Ho;
   const int bands = (Ho + BR - 1) / BR;
   BR = (Ho + bands - 1) / bands;   // balance the bands
-  const size_t smem = (size_t)((BR - 1) * stride + 3) * row_bytes;
-  const dim3 grid((unsigned)(C / 64), (unsigned)bands, (unsigned)batch);
+  const size_t band = (size_t)((BR - 1) * stride + 3) * row_bytes;
+  // frames per CTA (see the kernel): as many as keep >= 2 CTAs per SM's worth of work and fit the budget
+  static const int fpc_env = getenv("CASYNC_DW_FPC") ? atoi(getenv("CASYNC_DW_FPC")) : 0;   // developer A/B: 1, 2, 4
+  int fpc = fpc_env > 0 ? fpc_env : 4;   // measured at batch 64: the 12 launches sum to 226 (1) / 217 (2) / 217 us (4)
+  while (fpc > 1 && (band * fpc > (size_t)kDwSmemMax || batch < fpc)) fpc >>= 1;
+  const size_t smem = band * fpc;
+  const dim3 grid((unsigned)(C / 64), (unsigned)bands, (unsigned)((batch + fpc - 1) / fpc));
   const uint4* taps = reinterpret_cast<const uint4*>(wdp);
-  if (stride == 2) return (int)launch_pdl(dw3x3_kernel<2>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR);
-  return (int)launch_pdl(dw3x3_kernel<1>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR);
+#define DW_LAUNCH(S_, F_) \
+  return (int)launch_pdl(dw3x3_kernel<S_, F_>, grid, dim3(256), smem, st, in, out, taps, H, W, C, Ho, Wo, BR, batch)
+  if (stride == 2) {
+    if (fpc == 4) DW_LAUNCH(2, 4);
+    if (fpc == 2) DW_LAUNCH(2, 2);
+    DW_LAUNCH(2, 1);
+  }
+  if (fpc == 4) DW_LAUNCH(1, 4);
+  if (fpc == 2) DW_LAUNCH(1, 2);
+  DW_LAUNCH(1, 1);
+#undef DW_LAUNCH
 }
 
 // ---- paste-back blend -------------------------------------------------------------------------------------------------

@@ -54,6 +54,23 @@ def test_forward_matches_golden_and_oracle_stages(regime, monkeypatch):
             assert O.psnr_db(out[i], tgt[i]) >= MIN_PSNR
 
 
+@pytest.mark.parametrize("inctc", ["1", "0"])
+@pytest.mark.parametrize("batch", [3, 37])
+def test_input_block_on_tensor_cores(batch, inctc, monkeypatch):
+    """InConvDw (module/unet.py:58-67) as a strip_tc instantiation (fp32 input as bf16 hi + lo, biases on constant-one
+    channels, all three convolutions on tcgen05) and as round 1's inc_kernel (CASYNC_INCTC=0): stage x1 against the oracle.
+    Batches that are no multiple of anything: the CTAs' row ranges start and end inside frames and strips."""
+    monkeypatch.setenv("CASYNC_INCTC", inctc)
+    monkeypatch.setenv("CASYNC_SPLIT", "0")
+    model, sd = make_model("R1", seed=3)
+    x, a = O.make_inputs(batch, 5)
+    model(x.cuda(), a.cuda())
+    ref = torch.cat([O.forward(sd, x[i:i + 8], a[i:i + 8], return_stages=True)[1]["x1"] for i in range(0, batch, 8)])
+    err = O.rel_l2(stage_nchw(model, "x1", batch), ref)
+    print("\n[inc, INCTC=%s, B=%d] x1 rel-L2 = %.5f" % (inctc, batch, err))
+    assert err < 6e-3, err
+
+
 @pytest.mark.parametrize("regime", ["R0", "R1"])
 def test_config2_batch64_tolerance(regime):
     """BASELINE config 2: batch 64, bf16 on one B200 vs the fp32 reference arithmetic (oracle), default-init (R0) and
