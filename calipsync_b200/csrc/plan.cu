@@ -223,6 +223,9 @@ struct casync_plan {
   // the whole forward on two streams.  The low-resolution kernels are 100-450 CTAs of mostly fixed cost per launch, so
   // the halves' kernels share the GPU instead of leaving SMs idle.  Lane 0 = the caller's stream; lane 1 = `lane1`,
   // forked / joined with events, with its own side stream for the small-batch audio overlap.
+  bool hybrid = true;               // split batches: the 160/80/40-pixel stages (persistent kernels that fill the GPU on their
+                                    // own) run once for the whole batch, only the low-resolution middle runs as two lanes
+                                    // (CASYNC_HYBRID=0: the whole forward per lane)
   int split_min_batch = 24;         // CASYNC_SPLIT=0 disables, CASYNC_SPLIT=<n> sets the threshold
   cudaStream_t lane1 = nullptr, side1 = nullptr;
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_lane_go = nullptr, ev_lane_done = nullptr;
@@ -274,6 +277,10 @@ struct Workspace {
       o += align256((size_t)kBufs[i].rows * kBufs[i].cols * 2 * frames);
     }
     total = o;
+  }
+  // frames [frame0, ...) of an existing layout: every buffer is [frames][rows][cols], so a sub-batch is a slice
+  Workspace(const Workspace& full, int frame0) : base(full.base), total(full.total) {
+    for (int i = 0; i < kNumBufs; ++i) offs[i] = full.offs[i] + (size_t)kBufs[i].rows * kBufs[i].cols * 2 * frame0;
   }
   int index(const char* name) const {
     for (int i = 0; i < kNumBufs; ++i)
@@ -549,8 +556,10 @@ int run_up(const casync_plan* p, int level, const bf16* low, const bf16* skip, b
   return run_ir(p, i0 + 1, tmp, nullptr, out, kIr[i0 + 1].cout, w["h1"], w["h2"], nullptr, nullptr, batch, st);
 }
 
+enum : int { PH_HEAD = 1, PH_MID = 2, PH_TAIL = 4, PH_ALL = 7 };   // inc..down2 | down3..up1 | up2..output
+
 int forward_chunk(const casync_plan* p, const float* x, const float* audio, void* out, const Workspace& w, int batch,
-                  unsigned flags, cudaStream_t st, int lane = 0) {
+                  unsigned flags, cudaStream_t st, int lane = 0, int phases = PH_ALL) {
   int e;
   cudaStream_t const side = lane ? p->side1 : p->side;
   cudaEvent_t const ev_fork = lane ? p->ev_fork1 : p->ev_fork, ev_join = lane ? p->ev_join1 : p->ev_join;
@@ -560,6 +569,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     long l0;
     ~Count() { p->launches_chunk = launch_counter() - l0; }
   } count{p, launches0};
+  if (phases & PH_HEAD) {
   if (p->fuse_ir && p->inc_tc) {   // strip_tc.cu: all three convolutions of the input block on the tensor cores
     StripArgs f{};
     f.x_nchw = x;
@@ -577,6 +587,7 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     CK(launch_inc(x, w["x1"], p->w<uint8_t>("inc.inconv.0|w2t"), p->inc, batch, st));
   }
   prof_mark(p->fuse_ir && p->inc_tc ? "inc.striptc" : "inc.fused", 2.0 * batch * 25600 * (72 + 108 + 384), batch * 25600.0 * (24 + 64));
+  }
   const char* dn_t[4] = {"d1t", "d2t", "d3t", "d4t"};
   const char* dn_o[4] = {"x2", "x3", "x4", "cat"};
   const bf16* cur = w["x1"];
@@ -593,6 +604,32 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
     cur = w[dn_o[l]];
     return 0;
   };
+  if (phases != PH_ALL) {
+    // hybrid split (forward_eager): head and tail run once for the whole batch, the middle once per lane
+    if (phases & PH_HEAD) {
+      if ((e = down_block(0))) return e;
+      if ((e = down_block(1))) return e;
+    }
+    if (phases & PH_MID) {
+      cur = w["x3"];
+      if (overlap) {
+        CK(cudaEventRecord(ev_fork, st));
+        CK(cudaStreamWaitEvent(side, ev_fork, 0));
+        g_cap = p->overlap_cap ? p->num_sms / 2 : 0;
+        e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, side);
+        if (!e) e = run_kv(p, w["cat"], w, batch, side);
+        for (int l = 2; l < 4 && !e; ++l) e = down_block(l);
+        g_cap = 0;
+        if (e) return e;
+        CK(cudaEventRecord(ev_join, side));
+        CK(cudaStreamWaitEvent(st, ev_join, 0));
+      } else {
+        for (int l = 2; l < 4; ++l)
+          if ((e = down_block(l))) return e;
+        if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st))) return e;
+      }
+    }
+  } else {
   if ((e = down_block(0))) return e;
   if (overlap) {
     const int i0 = IR_DOWN + 2;   // down2.0 (fused, all SMs) still before the fork
@@ -614,12 +651,16 @@ int forward_chunk(const casync_plan* p, const float* x, const float* audio, void
       if ((e = down_block(l))) return e;
     if ((e = run_audio(p, audio, w["cat"] + 512, 1024, w, batch, st))) return e;
   }
+  }
+  if (phases & PH_MID) {
   if ((e = run_fusion_attention(p, w["cat"], w["kx"], w, batch, st, overlap))) return e;
   const char* fz[5] = {"kx", "f0", "f1", "f2", "fuse"};
   for (int l = 0; l < 4; ++l)
     if ((e = run_ir(p, IR_FUSE + l, w[fz[l]], nullptr, w[fz[l + 1]], kIr[IR_FUSE + l].cout, w["h1"], w["h2"], nullptr,
                     nullptr, batch, st))) return e;
   if ((e = run_up(p, 1, w["fuse"], w["x4"], w["t_up1"], w["up1"], w, batch, st))) return e;
+  }
+  if (!(phases & PH_TAIL)) return 0;
   if ((e = run_up(p, 2, w["up1"], w["x3"], w["t_up2"], w["up2"], w, batch, st))) return e;
   if ((e = run_up(p, 3, w["up2"], w["x2"], w["t_up3"], w["up3"], w, batch, st))) return e;
   g_final_done = false;
@@ -727,6 +768,7 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
     }
   }
   if (const char* c = getenv("CASYNC_GRAPH")) p->use_graphs = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_HYBRID")) p->hybrid = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_SPLIT")) p->split_min_batch = atoi(c) > 0 ? atoi(c) : (1 << 30);
   if (cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&p->lane1, cudaStreamNonBlocking) != cudaSuccess ||
@@ -868,7 +910,9 @@ size_t casync_stage_scratch_bytes(const casync_plan* plan, int batch) { return c
 
 int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
   if (!plan || batch <= 0) return 0;
-  int64_t per_chunk = 1 /*inc*/ + 1 /*audio prep*/ + 2 /*conv3, conv5*/ + 3 /*fc1, fc2, kv*/ + 4 * 3 /*attention*/ + 1 + 1;
+  // `mid`: launches of the low-resolution middle (down3 .. up1), which a split batch runs once per lane; `once`: the rest
+  int64_t mid = 1 /*audio prep*/ + 2 /*conv3, conv5*/ + 3 /*fc1, fc2, kv*/ + 4 * 3 /*attention*/ + 1 /*stage sum*/;
+  int64_t once = 1 /*inc*/ + 1 /*output head*/;
   for (int i = 1; i < kNumIr; ++i) {
     const IrDef& d = kIr[i];
     const bool up = i >= IR_UP && !((i - IR_UP) & 1);
@@ -877,14 +921,16 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
                         (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)) ||
                         (plan->strip_tc && strip_tc_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
     const bool dwe = plan->dw_epi && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
-    per_chunk += fused ? 1 : dwe ? 2 : 3;
+    const bool head_or_tail = (i >= IR_DOWN && i < IR_DOWN + 4) || i >= IR_UP + 2;   // down1, down2 | up2, up3, up4
+    (head_or_tail ? once : mid) += fused ? 1 : dwe ? 2 : 3;
   }
   if (plan->fuse_outc && plan->fuse_ir && plan->strip_tc && strip_tc_supported(32, 32, 160, 1, false, true))
-    per_chunk -= 1;   // the output head runs in the epilogue of up4.1
+    once -= 1;   // the output head runs in the epilogue of up4.1
   int64_t total = 0;
   for (int f0 = 0; f0 < batch; f0 += plan->chunk) {
     const int nb = batch - f0 < plan->chunk ? batch - f0 : plan->chunk;
-    total += per_chunk * (nb >= plan->split_min_batch ? 2 : 1);   // two lanes: every kernel twice
+    const bool split = nb >= plan->split_min_batch;   // two lanes: the middle (hybrid) or every kernel twice
+    total += split ? (plan->hybrid ? once + 2 * mid : 2 * (once + mid)) : once + mid;
   }
   return total;
 }
@@ -901,6 +947,27 @@ static int forward_eager(const casync_plan* plan, const float* x, const float* a
     if (nb >= plan->split_min_batch && !g_prof && plan->lane1) {
       // two lanes: frames [0, h0) on the caller's stream, [h0, nb) on the plan's second stream, joined at the end
       const int hcap = (cap + 1) / 2, h0 = (nb + 1) / 2, h1 = nb - h0;
+      if (plan->hybrid) {
+        // head (inc, down1, down2) and tail (up2..up4 + output head) once for all nb frames; the middle per lane on
+        // slices of the same layout
+        const Workspace wf(workspace, cap), v0(wf, 0), v1(wf, h0);
+        int e = forward_chunk(plan, xc, ac, oc, wf, nb, flags, st, 0, PH_HEAD);
+        if (e) return e;
+        const long l_head = plan->launches_chunk;
+        CK(cudaEventRecord(plan->ev_lane_go, st));
+        CK(cudaStreamWaitEvent(plan->lane1, plan->ev_lane_go, 0));
+        e = forward_chunk(plan, xc, ac, oc, v0, h0, flags, st, 0, PH_MID);
+        long l_mid = plan->launches_chunk;
+        if (!e) e = forward_chunk(plan, xc + (size_t)h0 * 6 * 25600, ac + (size_t)h0 * 32768, oc + (size_t)h0 * out_frame, v1,
+                                  h1, flags, plan->lane1, 1, PH_MID);
+        l_mid += plan->launches_chunk;
+        CK(cudaEventRecord(plan->ev_lane_done, plan->lane1));
+        CK(cudaStreamWaitEvent(st, plan->ev_lane_done, 0));
+        if (!e) e = forward_chunk(plan, xc, ac, oc, wf, nb, flags, st, 0, PH_TAIL);
+        if (e) return e;
+        plan->launches_chunk += l_head + l_mid;
+        continue;
+      }
       Workspace w0(workspace, hcap);
       Workspace w1(reinterpret_cast<uint8_t*>(workspace) + w0.total, hcap);
       CK(cudaEventRecord(plan->ev_lane_go, st));

@@ -97,7 +97,7 @@ def test_output_head_fused_into_the_last_decoder_block_is_bit_exact(batch, monke
     plain, _ = make_model("R1", seed=8)
     assert torch.equal(out_f, plain(xs, as_))
     assert torch.equal(u8_f, plain.forward_uint8(xs, as_))
-    assert fused.launches_per_forward(batch) == plain.launches_per_forward(batch) - (2 if batch >= 24 else 1)
+    assert fused.launches_per_forward(batch) == plain.launches_per_forward(batch) - 1   # (split batches: the tail runs once)
     ref = O.forward(sd, x, a)
     assert O.max_abs_255(out_f.cpu(), ref) <= MAX_ABS_255 and O.psnr_db(out_f.cpu(), ref) >= MIN_PSNR
 
@@ -322,23 +322,34 @@ def test_host_pipeline_frames_mode():
         assert torch.equal(o, model.forward_uint8(x, a).cpu())
 
 
+@pytest.mark.parametrize("hybrid", ["1", "0"])
 @pytest.mark.parametrize("batch", [25, 70])
-def test_two_lane_split_is_bit_exact(batch, monkeypatch):
-    """Batches >= 24 run as two half-batches on two streams.  Frames are independent, so the result must
-    equal the single-stream forward bit for bit -- odd batch sizes (unequal halves) included -- and the caller's stream
-    must see the joined result without an explicit synchronisation."""
+def test_two_lane_split_is_bit_exact(batch, hybrid, monkeypatch):
+    """Batches >= 24 run as two half-batches on two streams: the low-resolution middle only (hybrid, the
+    default: inc..down2 and up2..output run once for the whole batch) or the whole forward (CASYNC_HYBRID=0).  Frames
+    are independent, so the result must equal the single-stream forward bit for bit -- odd batch sizes (unequal halves)
+    included -- and the caller's stream must see the joined result without an explicit synchronisation.  With the
+    hybrid split the lanes work on slices of ONE workspace layout, so the stage tensors are comparable too."""
+    monkeypatch.setenv("CASYNC_HYBRID", hybrid)
     x, a = O.make_inputs(batch, 9)
     xs, as_ = x.cuda(), a.cuda()
     split, _ = make_model("R1", seed=3)
     out = split(xs, as_)
     doubled = out * 2.0                            # consumer on the caller's stream, enqueued right behind the forward
-    assert split.launches_per_forward(batch) == 2 * split.launches_per_forward(8)
+    n1 = split.launches_per_forward(8)
+    if hybrid == "0":
+        assert split.launches_per_forward(batch) == 2 * n1
+    else:
+        assert n1 < split.launches_per_forward(batch) < 2 * n1
+    stages = {n: split.stage(n, batch).clone() for n in ("x3", "kx", "up1", "up3")} if hybrid == "1" else {}
     monkeypatch.setenv("CASYNC_SPLIT", "0")
     single, _ = make_model("R1", seed=3)
     ref = single(xs, as_)
-    assert single.launches_per_forward(batch) == single.launches_per_forward(8)
+    assert single.launches_per_forward(batch) == n1
     assert torch.equal(out, ref)
     assert torch.equal(doubled, ref * 2.0)
+    for n, t in stages.items():
+        assert torch.equal(single.stage(n, batch), t), n
     assert torch.equal(split.forward_uint8(xs, as_), single.forward_uint8(xs, as_))
 
 
