@@ -42,11 +42,13 @@ def gather_frames(local: torch.Tensor, n_frames: int, dst: int = 0, group=None):
     return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
 
 
-def gather_chunked(produce, n_frames: int, batch: int, frame_shape, dtype, device, dst: int = 0, group=None):
+def gather_chunked(produce, n_frames: int, batch: int, frame_shape, dtype, device, dst: int = 0, group=None, out=None):
     """Rank's shard of an n_frames clip, produced in batches of `batch` frames; every finished batch is gathered to
     `dst` while the next one is being computed ("chunked and issued on a side stream so it overlaps
     the next chunk's compute").  `produce(lo, hi, out)` fills out[: hi - lo] with frames [lo, hi) of the clip (global
     indices).  All ranks issue the same number of equal-size collectives (ragged chunks travel zero padded).
+    `out` (multi-rank runs only): a caller-owned staging buffer [chunks, batch, *frame_shape] to reuse across calls --
+    stable addresses keep the CUDA graphs of the producing forwards valid.
     Returns the ordered [n_frames, *frame_shape] tensor on `dst`, None elsewhere."""
     import torch.distributed as dist
 
@@ -58,7 +60,9 @@ def gather_chunked(produce, n_frames: int, batch: int, frame_shape, dtype, devic
     n_local = sizes[rank]
     nchunks = -(-max(sizes) // batch) if max(sizes) else 0
     cuda = torch.device(device).type == "cuda"
-    out = torch.zeros((max(nchunks, 1), batch) + tuple(frame_shape), dtype=dtype, device=device)
+    shape = (max(nchunks, 1), batch) + tuple(frame_shape)
+    if out is None or not multi or tuple(out.shape) != shape or out.dtype != dtype:
+        out = torch.zeros(shape, dtype=dtype, device=device)
     recv = ([torch.empty_like(out) for _ in range(world)] if (multi and rank == dst) else None)
     side = torch.cuda.Stream(device) if (cuda and multi) else None
     for c in range(nchunks):
@@ -103,4 +107,14 @@ def synthesize_clip(model, crops_u8, hubert_feats, n_frames: int, batch: int = 6
         idx = torch.arange(lo, hi, device=dev, dtype=torch.int32)
         model.forward_frames(crops_u8[lo - lo0: hi - lo0], hubert_feats, idx, out=out[: hi - lo])
 
-    return gather_chunked(produce, n_frames, batch, (160, 160, 3), torch.uint8, dev, dst, group)
+    staging = None
+    if multi:   # one staging buffer per clip geometry, kept on the model (see gather_chunked)
+        cache = model.__dict__.setdefault("_clip_out", {})
+        key = (n_frames, batch, world, str(dev))
+        staging = cache.get(key)
+        if staging is None:
+            if len(cache) >= 2:
+                cache.pop(next(iter(cache)))
+            nchunks = max(1, -(-max(shard_sizes(n_frames, world)) // batch))
+            staging = cache[key] = torch.zeros((nchunks, batch, 160, 160, 3), dtype=torch.uint8, device=dev)
+    return gather_chunked(produce, n_frames, batch, (160, 160, 3), torch.uint8, dev, dst, group, out=staging)
