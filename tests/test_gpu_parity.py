@@ -302,6 +302,30 @@ def test_device_input_prologue_is_bit_exact_and_feeds_the_forward():
     assert torch.equal(u, model.forward_uint8(x, a))
 
 
+def test_forward_frames_staging_is_reused_safely():
+    """forward_frames assembles (x, audio) in model-owned buffers (stable CUDA-graph keys).  Back-to-back calls with
+    different inputs -- on one stream and on two streams without any synchronisation between them -- must each give the
+    result of a fresh model: the second call may only overwrite the staging once the first forward has consumed it."""
+    model, _ = make_model("R1", seed=6)
+    fresh, _ = make_model("R1", seed=6)
+    rs = np.random.RandomState(12)
+    feats = torch.from_numpy(rs.randn(50, 2, 1024).astype(np.float32)).cuda()
+    crops = [torch.from_numpy(rs.randint(0, 256, size=(6, 160, 160, 3), dtype=np.uint8)).cuda() for _ in range(4)]
+    idx = [torch.arange(6 * i, 6 * i + 6, dtype=torch.int32).cuda() for i in range(4)]
+    want = [fresh.forward_uint8(*fresh.prepare_inputs(crops[i], feats, idx[i])) for i in range(4)]
+    torch.cuda.synchronize()
+    got = [model.forward_frames(crops[0], feats, idx[0]), model.forward_frames(crops[1], feats, idx[1])]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for st, i in ((s1, 2), (s2, 3)):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            got.append(model.forward_frames(crops[i], feats, idx[i]))
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert torch.equal(got[i], want[i]), i
+    assert len(model._frame_io) == 1                  # one staging pair for the one batch size
+
+
 def test_host_pipeline_frames_mode():
     """frames mode of HostPipeline == prepare_inputs + forward_uint8 called directly."""
     from calipsync_b200 import HostPipeline
