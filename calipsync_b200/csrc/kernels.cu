@@ -2,6 +2,7 @@
 // stage sum + BN, output head.  All activations NHWC bf16, all arithmetic fp32.
 #include <cstdlib>
 #include "kernels.cuh"
+#include "gemm_dev.cuh"
 
 #include <cuda_bf16.h>
 
@@ -603,6 +604,55 @@ int launch_dw3x3(const __nv_bfloat16* in, __nv_bfloat16* out, const uint8_t* wdp
   if (fpc == 2) DW_LAUNCH(1, 2);
   DW_LAUNCH(1, 1);
 #undef DW_LAUNCH
+}
+
+// ---- decoder upsample + concat as its own pass --------------------------------------------------------------------------
+// thread = (pixel, 16-byte chunk c of the C2 upsampled channels): writes that chunk (bilinear x2 of `low`,
+// align_corners=True; the four tap weights as packed bf16 and an HFMA2 chain, the arithmetic of the fused kernels'
+// decoder producers) and copies chunk c of `skip` behind it.
+__global__ void __launch_bounds__(256) upcat_kernel(const __nv_bfloat16* __restrict__ low,
+                                                    const __nv_bfloat16* __restrict__ skip,
+                                                    __nv_bfloat16* __restrict__ out, int npix, int H, int C2) {
+  pdl_launch_dependents();
+  const int cpp = C2 >> 3;                      // 16-byte chunks per half
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int m = (int)(i / cpp), k = (int)(i - (long long)m * cpp) * 8;
+  if (m >= npix) return;
+  const int Hin = H >> 1;
+  const int x = m % H, t = m / H, y = t % H, b = t / H;
+  const float sy = (float)(Hin - 1) / (float)(H - 1) * (float)y, sx = (float)(Hin - 1) / (float)(H - 1) * (float)x;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Hin - 1 ? 1 : 0);
+  const float wy1 = sy - (float)y0, wy0 = 1.f - wy1, wx1 = sx - (float)x0, wx0 = 1.f - wx1;
+  const __nv_bfloat162 w00 = __float2bfloat162_rn(wy0 * wx0), w01 = __float2bfloat162_rn(wy0 * wx1),
+                       w10 = __float2bfloat162_rn(wy1 * wx0), w11 = __float2bfloat162_rn(wy1 * wx1);
+  pdl_wait();
+  const __nv_bfloat16* fb = low + (size_t)b * Hin * Hin * C2 + k;
+  const uint4 ta = __ldg(reinterpret_cast<const uint4*>(fb + (size_t)(y0 * Hin + x0) * C2));
+  const uint4 tb = __ldg(reinterpret_cast<const uint4*>(fb + (size_t)(y0 * Hin + x1) * C2));
+  const uint4 tc = __ldg(reinterpret_cast<const uint4*>(fb + (size_t)(y1 * Hin + x0) * C2));
+  const uint4 td = __ldg(reinterpret_cast<const uint4*>(fb + (size_t)(y1 * Hin + x1) * C2));
+  const uint4 sk = __ldg(reinterpret_cast<const uint4*>(skip + (size_t)m * C2 + k));
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ta);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&tb);
+  const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&tc);
+  const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&td);
+  uint4 o;
+  __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    po[j] = __hfma2(w11, pd[j], __hfma2(w10, pc[j], __hfma2(w01, pb[j], __hmul2(w00, pa[j]))));
+  __nv_bfloat16* op = out + (size_t)m * 2 * C2 + k;
+  *reinterpret_cast<uint4*>(op) = o;
+  *reinterpret_cast<uint4*>(op + C2) = sk;
+}
+
+int launch_upcat(const __nv_bfloat16* low, const __nv_bfloat16* skip, __nv_bfloat16* out, int batch, int H, int C2,
+                 cudaStream_t st) {
+  if (batch <= 0 || H < 2 || (H & 1) || (C2 & 7)) return (int)cudaErrorInvalidValue;
+  const int npix = batch * H * H;
+  const long long n = (long long)npix * (C2 >> 3);
+  return (int)launch_pdl(upcat_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, low, skip, out, npix, H, C2);
 }
 
 // ---- paste-back blend -------------------------------------------------------------------------------------------------

@@ -46,6 +46,10 @@ int launch_sum5(const __nv_bfloat16* tx, const __nv_bfloat16* o0, const __nv_bfl
 // sigmoid(outc_bn(outc(x)))  ->  fp32 NCHW [B,3,160,160] or uint8 HWC floor(p*255)
 int launch_outc(const __nv_bfloat16* x, void* out, const OutcParams& w, int batch, int u8_hwc, cudaStream_t st);
 // paste-back blend (infer_api.py:333-346): frames[region] = uint8(crop * m + frames[region] * (1 - m)) in float64
+// cat([bilinear x2 (align_corners) of low [B,H/2,W/2,C2], skip [B,H,W,C2]]) -> out [B,H,W,2*C2], NHWC bf16: the decoder's
+// upsample + concat (module/unet.py:82-97) materialised, same arithmetic as the GEMM's gathered A producer
+int launch_upcat(const __nv_bfloat16* low, const __nv_bfloat16* skip, __nv_bfloat16* out, int batch, int H, int C2,
+                 cudaStream_t st);
 int launch_blend_paste(uint8_t* frames, int H, int W, const uint8_t* crops, int ldc, const uint8_t* face, const float* soft,
                        const int* rects, int batch, cudaStream_t st);
 int kernels_init();

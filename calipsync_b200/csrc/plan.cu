@@ -223,6 +223,10 @@ struct casync_plan {
   // the whole forward on two streams.  The low-resolution kernels are 100-450 CTAs of mostly fixed cost per launch, so
   // the halves' kernels share the GPU instead of leaving SMs idle.  Lane 0 = the caller's stream; lane 1 = `lane1`,
   // forked / joined with events, with its own side stream for the small-batch audio overlap.
+  bool upcat_pass = true;           // decoder-first blocks on the GEMM path: materialise cat([up(low), skip]) first (CASYNC_UPCAT_PASS=0:
+                                    // gather it in the GEMM's A producer)
+  int unfuse_up2 = 1;               // up2.0 (256 -> 512 -> 64 at 40x40) as three launches + the pass above instead of the
+                                    // weight-streaming fused kernel (CASYNC_UNFUSE_UP2=0)
   bool hybrid = true;               // split batches: the 160/80/40-pixel stages (persistent kernels that fill the GPU on their
                                     // own) run once for the whole batch, only the low-resolution middle runs as two lanes
                                     // (CASYNC_HYBRID=0: the whole forward per lane)
@@ -333,7 +337,8 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
               2.0 * (px_in * d.cin * (up_low ? 0.625 : 1.0) + px_out * d.cout * (d.res ? 2 : 1)));
     return 0;
   }
-  if (p->fuse_ir && !post_s && ldc == d.cout && fused_ir_supported(d.cin, d.cout, d.stride, up_low != nullptr, d.res)) {
+  if (p->fuse_ir && !post_s && ldc == d.cout && !(p->unfuse_up2 && idx == IR_UP + 2) &&
+      fused_ir_supported(d.cin, d.cout, d.stride, up_low != nullptr, d.res)) {
     FusedArgs f{};
     f.in = in;
     f.low = up_low;
@@ -372,7 +377,17 @@ int run_ir(const casync_plan* p, int idx, const bf16* in, const bf16* up_low, bf
   g.ldc = hid;
   g.max_ctas = g_cap;
   g.dbg = gemm_dbg_for(short_name(d.name) + ".pw1");
-  if (up_low) {
+  if (up_low && p->upcat_pass && (size_t)H * H * (hid + d.cin) <= (size_t)25600 * 128) {   // (fits the h2 scratch)
+    // upsample + concat as its own pass into the far half of the h2 scratch (the block's depthwise output uses the
+    // near part): the GEMM then streams a plain TMA-fed A operand instead of gathering four taps per chunk in its
+    // producer warps, which ran at 2900 cycles per k-block against 512 of MMAs
+    bf16* cat = h2 + (size_t)batch * H * H * hid;
+    CK(launch_upcat(up_low, in, cat, batch, H, d.cin / 2, st));
+    prof_mark((short_name(d.name) + ".upcat").c_str(), 8.0 * batch * H * H * d.cin, 2.0 * batch * H * H * d.cin * 1.625);
+    g.amode = A_PLAIN;
+    g.A = cat;
+    g.lda = d.cin;
+  } else if (up_low) {
     g.amode = A_UPCAT;
     g.A = up_low;
     g.A2 = in;
@@ -769,6 +784,8 @@ int casync_plan_create(const void* host_blob, const void* dev_blob, size_t blob_
   }
   if (const char* c = getenv("CASYNC_GRAPH")) p->use_graphs = atoi(c) > 0;
   if (const char* c = getenv("CASYNC_HYBRID")) p->hybrid = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_UPCAT_PASS")) p->upcat_pass = atoi(c) > 0;
+  if (const char* c = getenv("CASYNC_UNFUSE_UP2")) p->unfuse_up2 = atoi(c);
   if (const char* c = getenv("CASYNC_SPLIT")) p->split_min_batch = atoi(c) > 0 ? atoi(c) : (1 << 30);
   if (cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&p->lane1, cudaStreamNonBlocking) != cudaSuccess ||
@@ -916,13 +933,13 @@ int64_t casync_launches_per_forward(const casync_plan* plan, int batch) {
   for (int i = 1; i < kNumIr; ++i) {
     const IrDef& d = kIr[i];
     const bool up = i >= IR_UP && !((i - IR_UP) & 1);
-    const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) &&
+    const bool fused = plan->fuse_ir && i != IR_AUD7 && !(i == IR_DOWN + 7) && !(plan->unfuse_up2 && i == IR_UP + 2) &&
                        (fused_ir_supported(d.cin, d.cout, d.stride, up, d.res) ||
                         (plan->strip_ir && strip_ir_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)) ||
                         (plan->strip_tc && strip_tc_supported(d.cin, d.cout, d.h_in, d.stride, up, d.res)));
     const bool dwe = plan->dw_epi && !up && d.stride == 1 && d.h_in * d.h_in <= 100 && (2 * d.cin) % 256 == 0;
     const bool head_or_tail = (i >= IR_DOWN && i < IR_DOWN + 4) || i >= IR_UP + 2;   // down1, down2 | up2, up3, up4
-    (head_or_tail ? once : mid) += fused ? 1 : dwe ? 2 : 3;
+    (head_or_tail ? once : mid) += fused ? 1 : (dwe ? 2 : 3) + (up && plan->upcat_pass && d.h_in <= 80 ? 1 : 0);
   }
   if (plan->fuse_outc && plan->fuse_ir && plan->strip_tc && strip_tc_supported(32, 32, 160, 1, false, true))
     once -= 1;   // the output head runs in the epilogue of up4.1
