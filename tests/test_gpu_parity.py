@@ -102,6 +102,37 @@ def test_output_head_fused_into_the_last_decoder_block_is_bit_exact(batch, monke
     assert O.max_abs_255(out_f.cpu(), ref) <= MAX_ABS_255 and O.psnr_db(out_f.cpu(), ref) >= MIN_PSNR
 
 
+@pytest.mark.parametrize("batch", [5, 33])
+def test_no_writes_outside_the_callers_buffers(batch):
+    """Canary regions around the output tensor and the workspace handed to casync_forward (C ABI, unsplit and two-lane
+    batches, fp32 and uint8 outputs) must stay untouched, and results must not depend on what the workspace held."""
+    import ctypes
+    from calipsync_b200 import _lib
+    model, _ = make_model("R1", seed=9)
+    x, a = O.make_inputs(batch, 17)
+    xs, as_ = x.cuda(), a.cuda()
+    want = model(xs, as_)                                  # creates the plan
+    lib, plan = _lib.load(), model._plan[0]
+    pad = 1 << 20
+    ws_bytes = lib.casync_workspace_bytes(plan, batch)
+    ws = torch.full((ws_bytes + 2 * pad,), 0xA5, dtype=torch.uint8, device="cuda")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for flags, frame_bytes in ((_lib.F_BF16, 3 * 160 * 160 * 4), (_lib.F_OUT_U8_HWC, 160 * 160 * 3)):
+        out = torch.full((batch * frame_bytes + 2 * pad,), 0x5A, dtype=torch.uint8, device="cuda")
+        assert (ws.data_ptr() + pad) % 256 == 0 and (out.data_ptr() + pad) % 256 == 0
+        rc = lib.casync_forward(plan, xs.data_ptr(), as_.data_ptr(), out.data_ptr() + pad, ws.data_ptr() + pad, batch, flags,
+                                stream)
+        _lib.check(rc, "casync_forward")
+        torch.cuda.synchronize()
+        assert bool((out[:pad] == 0x5A).all()) and bool((out[-pad:] == 0x5A).all())
+        assert bool((ws[:pad] == 0xA5).all()) and bool((ws[-pad:] == 0xA5).all())
+        body = out[pad: pad + batch * frame_bytes]
+        if flags == _lib.F_BF16:
+            assert torch.equal(body.view(torch.float32).view(batch, 3, 160, 160), want)
+        else:
+            assert torch.equal(body.view(batch, 160, 160, 3), model.forward_uint8(xs, as_))
+
+
 def test_frames_are_independent_and_ragged_batches_work():
     """Any batch size (not a multiple of the 128-row tiles), and frame i does not depend on its batch mates:
     the property frame sharding relies on (bit-exact, same kernels and per-row arithmetic)."""
