@@ -1,5 +1,6 @@
 // Strip-streaming fused InvertedResidual with the depthwise 3x3 ON THE TENSOR CORES, for the blocks with 64 hidden
-// channels (up4.1, up3.1, audio conv1).  Same geometry as strip_ir.cu (strips of SW output columns, a contiguous range of
+// channels (up4.1 -- with the network's output head in its epilogue --, up3.1, audio conv1) and, as the INC instantiation
+// (16 padded hidden channels, fp32 NCHW input; see TCfg), for the input block.  Same geometry as strip_ir.cu (strips of SW output columns, a contiguous range of
 // the global padded-row list per CTA, hidden positions in 128-row tiles), but the depthwise conv is 9 taps x 4 channel
 // groups of
 //     DW[tile][:, 16g..16g+15] += HID[rows shifted by dy*WW+dx][:, 16g..16g+15] . diag(w[tap, 16g..16g+15])
