@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmArgs p, 
 }
 
 int g_num_sms = 148;
+thread_local int g_cost_cap = 0;   // gemm_set_cost_cap
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -592,6 +593,7 @@ static int gemm_encode_store_map(void* tm_out, const __nv_bfloat16* Cp, int rows
 }
 
 int gemm_num_sms() { return g_num_sms; }
+void gemm_set_cost_cap(int ctas) { g_cost_cap = ctas; }
 
 namespace {
 
@@ -689,13 +691,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   const long mt = (a.M + kBM - 1) / kBM;
   const int cap = a.max_ctas > 0 && a.max_ctas < g_num_sms ? a.max_ctas : g_num_sms;
+  // tile shape: while two lanes share the GPU (plan.cu, split batches) a launch gets about half of the SMs, and the wave
+  // count is computed for that share (measured: 1.798 -> 1.789 ms at batch 64, 1.082 -> 1.059 at 32, 6.567 -> 6.495 at 256;
+  // for an unsplit batch 8 the same assumption costs 4 %, so it is tied to the split)
+  const int ccap = g_cost_cap > 0 && g_cost_cap < cap ? g_cost_cap : cap;
   int best = 32;
-  double bc = tile_cost(mt, a.N, 32, cap);
+  double bc = tile_cost(mt, a.N, 32, ccap);
   static const int bn_max = getenv("CASYNC_GEMM_BNMAX") ? atoi(getenv("CASYNC_GEMM_BNMAX")) : 256;   // developer A/B
   for (int bn : {64, 128, 192, 256}) {   // 192: N = 576 (p_1 + q) -> 3 column tiles instead of 9
     if (bn > bn_max) continue;
     if (a.vt && a.vt_col0 % bn) continue;   // a column tile must not straddle the row-major | transposed boundary
-    const double c = tile_cost(mt, a.N, bn, cap);
+    const double c = tile_cost(mt, a.N, bn, ccap);
     if (c <= bc) {
       bc = c;
       best = bn;

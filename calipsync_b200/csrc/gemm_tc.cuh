@@ -44,6 +44,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream);  // returns 0 or cudaEr
 int gemm_init();                                          // set smem attributes (once per process)
 // 2-D TMA tensor map over a row-major bf16 matrix [rows, cols] with pitch ld (elements): box = 64 columns x box_rows
 // rows, SWIZZLE_128B or unswizzled.  tm_out: 128-byte CUtensorMap, 64-byte aligned.  Needs gemm_init().
+// SMs a launch may count on when it chooses its tile shape (0 = all): set around work that shares the GPU with another lane
+void gemm_set_cost_cap(int ctas);
 int gemm_encode_map(void* tm_out, const __nv_bfloat16* A, int rows, int cols, int ld, int box_rows, bool swizzle128);
 int gemm_num_sms();
 

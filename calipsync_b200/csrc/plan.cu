@@ -973,10 +973,12 @@ static int forward_eager(const casync_plan* plan, const float* x, const float* a
         const long l_head = plan->launches_chunk;
         CK(cudaEventRecord(plan->ev_lane_go, st));
         CK(cudaStreamWaitEvent(plan->lane1, plan->ev_lane_go, 0));
+        gemm_set_cost_cap(plan->num_sms / 2);   // the two lanes share the GPU
         e = forward_chunk(plan, xc, ac, oc, v0, h0, flags, st, 0, PH_MID);
         long l_mid = plan->launches_chunk;
         if (!e) e = forward_chunk(plan, xc + (size_t)h0 * 6 * 25600, ac + (size_t)h0 * 32768, oc + (size_t)h0 * out_frame, v1,
                                   h1, flags, plan->lane1, 1, PH_MID);
+        gemm_set_cost_cap(0);
         l_mid += plan->launches_chunk;
         CK(cudaEventRecord(plan->ev_lane_done, plan->lane1));
         CK(cudaStreamWaitEvent(st, plan->ev_lane_done, 0));
