@@ -133,6 +133,24 @@ def test_no_writes_outside_the_callers_buffers(batch):
             assert torch.equal(body.view(batch, 160, 160, 3), model.forward_uint8(xs, as_))
 
 
+def test_decoder_first_block_paths_agree(monkeypatch):
+    """up1.0 / up2.0 run as upsample-concat pass + TMA-fed GEMM + depthwise + GEMM (default).  The older paths -- concat
+    gathered in the GEMM's A producer (fp32 taps), up2.0 on the weight-streaming fused kernel -- stay selectable and must
+    give the same image within bf16 noise, each within the tolerance against the oracle."""
+    x, a = O.make_inputs(6, 23)
+    new, sd = make_model("R1", seed=10)
+    out_new = new(x.cuda(), a.cuda()).cpu()
+    monkeypatch.setenv("CASYNC_UPCAT_PASS", "0")
+    monkeypatch.setenv("CASYNC_UNFUSE_UP2", "0")
+    old, _ = make_model("R1", seed=10)
+    out_old = old(x.cuda(), a.cuda()).cpu()
+    assert new.launches_per_forward(6) == old.launches_per_forward(6) + 4      # + 2 passes, up2.0: 1 -> 3 launches
+    ref = O.forward(sd, x, a)
+    for out in (out_new, out_old):
+        assert O.max_abs_255(out, ref) <= MAX_ABS_255 and O.psnr_db(out, ref) >= MIN_PSNR
+    assert O.max_abs_255(out_new, out_old) <= 0.5 and O.psnr_db(out_new, out_old) >= 60.0
+
+
 def test_frames_are_independent_and_ragged_batches_work():
     """Any batch size (not a multiple of the 128-row tiles), and frame i does not depend on its batch mates:
     the property frame sharding relies on (bit-exact, same kernels and per-row arithmetic)."""
